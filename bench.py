@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py -- MARCONet inference hot path on B200 (metric: SR chars/s, 128-px-high output).
+
+A "step" is one pass of the full hot path (TextContextEncoderV2 -> TSPGAN -> TSPSRNet, the data flow of the
+reference's test_sr.py:145-197) over one batch of synthetic 32x512 LR text lines with 16 characters each
+(BASELINE.json configs[1]; --lines sets lines per GPU per step).  One process per GPU; lines are independent
+(test_sr.py:77) so ranks shard lines with no data-path collective ("weak" scaling).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--lines L] [--chars C]
+
+Prints ONE JSON line on rank 0.  See DESIGN.md "Measurement" for how every field is produced.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# algorithmic work, SURVEY.md section 8d (2*MAC of every conv/linear/matmul of the reference modules)
+GF_ENCODER_LINE = 111.692
+GF_TSPGAN_CHAR = 41.785
+GF_SR_LINE = 484.146
+GF_SR_CHAR = 47.245
+
+
+def gflop_per_line(chars):
+    return GF_ENCODER_LINE + GF_SR_LINE + (GF_TSPGAN_CHAR + GF_SR_CHAR) * chars
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([f.strip() for f in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        sm, mx, reasons = [], 0, set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[0])); mx = max(mx, float(s[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=mx or None, reasons=sorted(reasons), samples=len(sm))
+
+
+def make_inputs(lines, chars, seed):
+    from oracle import synth   # seeded synthetic input generators only (no oracle compute on this leg)
+    lq = synth.make_lq(lines, seed)
+    labels = [synth.make_labels(chars, seed + b) for b in range(lines)]
+    locs = synth.make_locs(lines, chars)
+    return lq, labels, locs
+
+
+# --------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle port (the reference is Python and cannot travel to the GPU box;
+# oracle/restate.py is bit-identical to its modules, tests/test_oracle.py) on all host cores.
+# --------------------------------------------------------------------------------------------
+def cpu_line_seconds(chars, repeats=1, threads=None):
+    import torch
+    from oracle import restate, synth
+    threads = threads or (os.cpu_count() or 1)
+    torch.set_num_threads(threads)
+    sds = synth.make_checkpoints(0)
+    lq, labels, locs = make_inputs(1, chars, 0)
+    best = None
+    with torch.no_grad():
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            restate.full_line(sds, lq, labels, locs)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    return best, threads
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    chars = args.chars
+    budget_s = 150.0
+    t_first, threads = cpu_line_seconds(chars, 1)                      # warm-up step (also sizes the run)
+    steps = max(1, min(args.steps, int(budget_s // max(t_first, 1e-3))))
+    times = []
+    for _ in range(steps):
+        t, _ = cpu_line_seconds(chars, 1)
+        times.append(t)
+    ms = 1e3 * sum(times) / len(times)
+    value = chars / (ms / 1e3)
+    rec = {
+        "impl": "reference", "metric": "sr_chars_per_sec", "value": value, "unit": "chars/s", "n_gpus": 0, "steps": steps,
+        "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"1 synthetic 32x512 LR line x {chars} chars, encoder->TSPGAN->TSPSRNet (BASELINE configs[1])",
+                   "lines_per_step": 1, "chars_per_line": chars},
+        "cpu_baseline": {"value": value, "unit": "chars/s", "cores": threads, "kind": "port",
+                         "sample": f"{steps} x one full {chars}-char line through oracle/restate.py (bit-identical restatement of the "
+                                   f"reference's torch CPU path), torch {torch.__version__}, {threads} threads"},
+        "e2e": {"value": value, "unit": "chars/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(rec), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from marconet_b200 import _lib, ops
+    from marconet_b200.models import networks
+    from oracle import synth   # synthetic checkpoint generator (weights only)
+
+    _lib.load()   # fail loudly if the CUDA library is missing
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if args.precision is not None:
+        ops.set_default_precision(args.precision)
+
+    sds = synth.make_checkpoints(0)
+    nets = {}
+    for key, cls in (("tspgan", networks.TSPGAN), ("encoder", networks.TextContextEncoderV2), ("sr", networks.TSPSRNet)):
+        m = cls()
+        m.load_state_dict(sds[key], strict=True)
+        nets[key] = m.eval().to(dev)
+
+    lines, chars = args.lines, args.chars
+    lq_h, labels, locs_h = make_inputs(lines, chars, seed=100 * rank)
+    lq_pin, locs_pin = lq_h.pin_memory(), locs_h.pin_memory()
+    lab_dev = [l.to(dev) for l in labels]
+    lq_dev, locs_dev = lq_pin.to(dev), locs_pin.to(dev)
+
+    def step(lq, locs):
+        _, _, w = nets["encoder"](lq)
+        p64, p32 = [], []
+        for b in range(lines):
+            _, f64, f32_ = nets["tspgan"](styles=w[b:b + 1].expand(chars, -1), labels=lab_dev[b], noise=None)
+            p64.append(f64); p32.append(f32_)
+        return nets["sr"](lq, p64, p32, locs)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for _ in range(steps):
+            fn()
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        barrier()
+        return ms
+
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            step(lq_dev, locs_dev)
+        sampler = ClockSampler(local)
+        sampler.start()
+        l0 = ops.LAUNCHES
+        ms_total = timed(lambda: step(lq_dev, locs_dev), args.steps)
+        launches = (ops.LAUNCHES - l0) // args.steps
+        clocks = sampler.summary()
+
+        # e2e: host buffers in, SR image out, copies inside the timed region
+        sr_host = torch.empty((lines, 3, 128, 2048), dtype=torch.float32).pin_memory()
+
+        def e2e_step():
+            lq = lq_pin.to(dev, non_blocking=True)
+            locs = locs_pin.to(dev, non_blocking=True)
+            sr = step(lq, locs)
+            sr_host.copy_(sr, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        e2e_step()
+        ms_e2e = timed(e2e_step, args.steps)
+
+        roof = modconv_roofline(nets["tspgan"], chars, dev) if rank == 0 else None
+
+    total_chars = world * lines * chars
+    ms_step = ms_total / args.steps
+    value = total_chars / (ms_step / 1e3)
+    e2e_value = total_chars / (ms_e2e / args.steps / 1e3)
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            t, threads = cpu_line_seconds(chars, 1)
+            cpu = {"value": chars / t, "unit": "chars/s", "cores": threads, "kind": "port",
+                   "sample": f"one full {chars}-char 32x512 line through oracle/restate.py (torch CPU fp32, {threads} threads)"}
+        rec = {
+            "metric": "sr_chars_per_sec", "value": value, "unit": "chars/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{lines} synthetic 32x512 LR line(s) x {chars} chars per GPU per step, "
+                                   f"encoder->TSPGAN->TSPSRNet (BASELINE configs[1])",
+                       "lines_per_step_per_gpu": lines, "chars_per_line": chars, "parallelism": f"line-sharded dp{world}, no collective",
+                       "precision": {0: "fp32 CUDA-core", 1: "fp16x3 tcgen05", 2: "bf16x3 tcgen05", 3: "fp16 tcgen05"}[ops.default_precision()],
+                       "l2": "weights (352 MB fp32) + activations (>1 GB/line) exceed the 126 MB L2; no flush needed",
+                       "gflop_per_step_per_gpu": gflop_per_line(chars) * lines,
+                       "achieved_tflops_per_gpu": gflop_per_line(chars) * lines / ms_step},
+            "ms_per_line": ms_step / lines,
+            "e2e": {"value": e2e_value, "unit": "chars/s", "h2d_bytes_per_step": int(lq_pin.numel() * 4 + locs_pin.numel() * 4),
+                    "d2h_bytes_per_step": int(sr_host.numel() * 4)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(rec), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def modconv_roofline(tspgan, chars, dev, iters=20):
+    """Live CUDA-event timing of the dominant kernel: the 3x3 modulated conv 512->512 at 32x32 for `chars`
+    characters (reference networks.py:294,299 grouped conv; 4.83 GFLOP per character and launch)."""
+    import torch
+    from marconet_b200 import ops
+    peaks = load_peaks()
+    gen = tspgan.TextGenerator
+    pk = gen._get_packed(dev)
+    e = pk["styled"][6]                                   # convs.5: 512->512 @ 32x32, no upsample
+    x = torch.randn(chars, 32, 32, 512, device=dev)
+    dm = torch.rand(chars, 512, device=dev) + 0.5
+    flush = torch.empty(64 << 20, dtype=torch.float32, device=dev)   # 256 MB > L2
+    st = torch.cuda.current_stream()
+    tot = 0.0
+    for i in range(iters + 3):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        ops.conv2d(x, e["w"], 3, 3, pad=(1, 1), bias=e["bias"], out_scale=dm, act=ops.ACT_LRELU02, gain=2 ** 0.5)
+        e1.record(st)
+        torch.cuda.synchronize()
+        if i >= 3:
+            tot += e0.elapsed_time(e1)
+    ms = tot / iters
+    flops = 2.0 * 512 * 512 * 9 * 32 * 32 * chars
+    achieved = flops / (ms * 1e-3) / 1e12
+    return {"kernel": "mn_conv2d_nhwc modulated 3x3 512->512 @32x32 x%d chars" % chars, "bound": "tensor", "achieved": achieved,
+            "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_burst"], "traffic": None,
+            "ms_per_launch": ms, "peak_source": peaks["source"] + ", bf16 burst (kernel timed alone, L2 flushed)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--lines", type=int, default=1, help="LR lines per GPU per step")
+    ap.add_argument("--chars", type=int, default=16)
+    ap.add_argument("--precision", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

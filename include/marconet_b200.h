@@ -1,0 +1,189 @@
+/*
+ * marconet_b200.h -- C ABI of libmarconet_b200.so (sm_100a).
+ *
+ * The reference (csxmli2016/MARCONet) has no FFI/plugin boundary of its own: its hot
+ * path is Python modules in models/networks.py that call torch.nn.functional ops
+ * (cuDNN / cuBLAS / ATen kernels) plus one third-party CUDA extension
+ * (basicsr.ops.fused_act, models/networks.py:10).  This header is the boundary a
+ * maintainer would bind instead of those calls: every entry point names the
+ * reference call site(s) it replaces.  All functions
+ *   - take raw DEVICE pointers and sizes (no torch types),
+ *   - are asynchronous on the given stream (a cudaStream_t passed as void*),
+ *   - never allocate persistent device memory (the caller owns every buffer,
+ *     including workspaces),
+ *   - return 0 on success or a negative mn_status; mn_last_error() returns a
+ *     message for the calling thread.
+ *
+ * Activation layout everywhere: NHWC, fp32, channel stride given explicitly as
+ * `*_cs` (floats per pixel in the underlying buffer) so that operators can read
+ * from / write into channel slices of concatenated buffers without copies.
+ */
+#ifndef MARCONET_B200_H
+#define MARCONET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    MN_OK = 0,
+    MN_ERR_INVALID = -1,   /* bad argument (shape, alignment, null pointer)      */
+    MN_ERR_CUDA = -2,      /* a CUDA runtime/driver call failed (see last error) */
+    MN_ERR_UNSUPPORTED = -3,
+    MN_ERR_WORKSPACE = -4  /* workspace too small                                 */
+} mn_status;
+
+typedef enum {
+    MN_ACT_NONE = 0,
+    MN_ACT_RELU = 1,       /* models/resnet.py:24,29                              */
+    MN_ACT_LRELU02 = 2,    /* nn.LeakyReLU(0.2) / fused_leaky_relu slope          */
+    MN_ACT_TANH = 3,       /* models/networks.py:321,375                          */
+    MN_ACT_GELU = 4,       /* exact erf GELU, models/textvit_arch.py:47,87        */
+    MN_ACT_SIGMOID = 5,    /* models/textvit_arch.py:50                           */
+    MN_ACT_RSQRT_EPS = 6   /* rsqrt(v + 1e-8): demodulation, networks.py:286      */
+} mn_act;
+
+typedef enum {
+    MN_PREC_FP32_SIMT = 0,   /* CUDA-core fp32 FMA implicit GEMM                       */
+    MN_PREC_F16X3_TC = 1,    /* tcgen05 kind::f16, fp16 hi/lo split, 3 MMAs (~fp32)    */
+    MN_PREC_BF16X3_TC = 2,   /* tcgen05 kind::f16, bf16 hi/lo split, 3 MMAs            */
+    MN_PREC_F16X1_TC = 3     /* tcgen05 single pass fp16 (NOT parity grade)            */
+} mn_precision;
+
+const char* mn_last_error(void);
+int mn_version(void);
+/* 1 when the current device is compute capability 10.x (tcgen05/TMA paths usable). */
+int mn_device_is_sm100(void);
+
+/* ------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution / linear layer.
+ *
+ * Replaces: every F.conv2d / nn.Conv2d / nn.Linear / F.linear on the path
+ *   models/resnet.py:5-8,36,21-30 ; models/networks.py:294,299 (ModulatedConv2d, via the
+ *   shared-weight reformulation y = demod[n,o] * sum_k W[o,k] * (s[n,c(k)] * x[n,k]) ),
+ *   :336-408,501-505 (TSPSRNet convs, spectral norm folded at pack time),
+ *   models/textvit_arch.py:34,42,46-51,57,61,86-88,101-102 (Linear = 1x1 conv on [M,1,1,K]),
+ *   and the fused bias+leaky-relu of basicsr fused_act (networks.py:195,244-245).
+ *
+ *   y[n,oy,ox,o] = act( out_scale[n,o] * sum_{ky,kx,c} x[n,oy*sh+ky-ph,ox*sw+kx-pw,c] * w[(ky*KW+kx)*Cin+c][o]
+ *                       + bias[o] + residual[n,oy,ox,o] ) * act_gain
+ *   y2[n,oy,ox,o] = y[n,oy,ox,o] * y2_scale[n,o]      (optional second output: the
+ *                   pre-modulated operand of the next modulated conv)
+ *   Columns ox >= valid_w[n] are written as 0 when valid_w != NULL (ragged per-character
+ *   windows keep their zero padding, models/networks.py:442-447).
+ * ------------------------------------------------------------------------------------ */
+typedef struct {
+    const float* x;  int N, H, W, Cin, x_cs;
+    const float* w;  int KH, KW, stride_h, stride_w, pad_h, pad_w, Cout;   /* w: [KH*KW*Cin][Cout] */
+    float* y;        int y_cs;                 /* may be NULL when only y2 is wanted           */
+    const float* bias;                         /* [Cout] or NULL                               */
+    const float* out_scale; int out_scale_stride; /* [N][stride] (stride 0 -> Cout) or NULL      */
+    const float* residual; int res_cs;         /* NHWC [N,OH,OW,res_cs] or NULL                */
+    int res_broadcast_n;                       /* 1: residual has no batch dim (positional emb) */
+    int act;  float act_gain;
+    float* y2;       int y2_cs;  const float* y2_scale; int y2_scale_stride;   /* optional      */
+    const int32_t* valid_w;                    /* [N] or NULL                                   */
+    float* workspace; int64_t workspace_bytes; /* split-K partial sums; may be NULL (no split)  */
+    int split_k;                               /* 0 = choose automatically, 1 = never split     */
+    int precision;                             /* mn_precision                                  */
+} mn_conv_params;
+
+int mn_conv2d_nhwc(const mn_conv_params* p, void* stream);
+/* Bytes of workspace mn_conv2d_nhwc wants for this problem (0 if it will not split). */
+int64_t mn_conv2d_workspace_bytes(const mn_conv_params* p);
+
+/* ------------------------------------------------------------------------------------
+ * Generator (TSPGAN) operators
+ * ------------------------------------------------------------------------------------ */
+/* PixelNorm, models/networks.py:170-171:  y = x * rsqrt(mean(x^2, dim=1) + 1e-8), x:[N][C]. */
+int mn_pixelnorm(const float* x, float* y, int N, int C, void* stream);
+
+/* SelectText (models/networks.py:205-215) fused with the first conv's input modulation:
+ *   out[n, yy, l*4+xx, c] = emb[labels[n*L+l]][c] * s[n*s_stride + c],   yy,xx in [0,4)
+ * labels are int64 on the DEVICE and must already be range-checked by the host. */
+int mn_select_text(const float* emb, const int64_t* labels, const float* s, int s_stride,
+                   float* out, int N, int L, int C, void* stream);
+
+/* Demodulation factors, models/networks.py:284-287 restated on the shared weight:
+ *   demod[n][o] = rsqrt( sum_c s[n][c]^2 * wsq[c][o] + 1e-8 ),
+ *   wsq[c][o] = scale^2 * sum_{ky,kx} W[o][c][ky][kx]^2 (packed once at load time). */
+int mn_demod(const float* s, int s_stride, const float* wsq, float* demod, int N, int Cin, int Cout, void* stream);
+
+/* y = (bilinear x2 upsample, align_corners=False, of x) * s[n][c]   (up=1)
+ * y = x * s[n][c]                                                   (up=0);  s may be NULL.
+ * Replaces nn.Upsample / F.interpolate(scale_factor=2, mode='bilinear') at
+ * models/networks.py:268,293,318,360,370,415-416 (and the per-sample style multiply of :284). */
+int mn_resample_modulate(const float* x, int x_cs, float* y, int y_cs, const float* s, int s_stride,
+                         int N, int H, int W, int C, int up, void* stream);
+
+/* ToRGB, models/networks.py:313-321: 1x1 modulated conv to 3 channels WITHOUT demodulation
+ * + bias + bilinear-x2(skip) + tanh.
+ *   out[n,p,o] = tanh( sum_c x[n,p,c]*s[n][c]*w[o][c] + bias[o] + up2(skip)[n,p,o] )
+ * w:[3][C] already multiplied by 1/sqrt(C); skip:[N,H/2,W/2,3] or NULL; out:[N,H,W,3]. */
+int mn_torgb(const float* x, int x_cs, const float* s, int s_stride, const float* w, const float* bias,
+             const float* skip, float* out, int N, int H, int W, int C, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * SR decoder (TSPSRNet) operators
+ * ------------------------------------------------------------------------------------ */
+/* GroupNorm(32 channels/group, eps) + optional swish, models/networks.py:487-493,508-512.
+ * Statistics run over H x valid_w[n] pixels per sample (valid_w NULL -> W); columns beyond
+ * valid_w[n] are written as 0.  stats_ws: >= N*(C/cpg)*2 doubles. */
+int mn_groupnorm_swish(const float* x, int x_cs, float* y, int y_cs, const float* gamma, const float* beta,
+                       int N, int H, int W, int C, int cpg, float eps, int swish,
+                       const int32_t* valid_w, double* stats_ws, void* stream);
+
+/* Per-character window table entry (host computes the integers bit-exactly like
+ * models/networks.py:426-441 / :460-474). */
+typedef struct {
+    int32_t line;     /* b: which LR line the character belongs to                          */
+    int32_t x1, x2;   /* window [x1,x2) in the line feature map                              */
+    int32_t y1;       /* first column of the centred crop of the character prior            */
+} mn_window;
+
+/* AdaIN + concat, models/networks.py:442-445,518-533:
+ *   out[i,:,:wv,0:C]  = (prior[i,:,y1:y1+wv,:] - mean_p)/std_p * std_l + mean_l
+ *   out[i,:,:wv,C:2C] = feat[line,:,x1:x2,:]
+ *   out[i,:,wv:,:]    = 0                        (wv = x2-x1, slot width = Wp)
+ * std uses the unbiased variance + 1e-5.  prior:[Nc,H,Wp,C], feat:[B,H,W,C], out:[Nc,H,Wp,2C]. */
+int mn_adain_concat(const float* prior, int prior_cs, const float* feat, int feat_cs, const mn_window* win,
+                    float* out, int Nc, int H, int Wp, int W, int C, void* stream);
+
+/* Write-back of the per-character modulation, models/networks.py:448-449 / :481-482:
+ *   out[b,:,x,:] = feat + (feat*scale[i,:,x-x1,:] + shift[i,:,x-x1,:])  if column x of line b is
+ *   owned by character i = owner[b*W + x] (the LAST character in program order whose window
+ *   covers x; -1: none -> out = feat).  scale/shift:[Nc,H,Wp,C]. */
+int mn_window_scatter(const float* feat, int feat_cs, const float* scale, const float* shift,
+                      const int32_t* owner, const mn_window* win, float* out, int out_cs,
+                      int B, int H, int W, int Wp, int C, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * TextViT operators
+ * ------------------------------------------------------------------------------------ */
+/* nn.LayerNorm over the last dim (eps 1e-5), models/textvit_arch.py:41,46,53,58,85,99. */
+int mn_layernorm(const float* x, float* y, const float* gamma, const float* beta, int rows, int dim,
+                 float eps, void* stream);
+
+/* LayerNorm over the TOKEN axis followed by Linear(T -> To) over the token axis, i.e. the
+ * `x.permute(0,2,1)` -> LayerNorm(T) -> Linear -> permute(0,2,1) idiom at
+ * models/textvit_arch.py:154 (T=64 -> 16) and :72 (64 -> 1).  x:[B,T,D] -> out:[B,To,D]. */
+int mn_token_mix(const float* x, const float* gamma, const float* beta, const float* w, const float* bias,
+                 float* out, int B, int T, int To, int D, float eps, void* stream);
+
+/* Fused multi-head attention, models/textvit_arch.py:104-111: softmax(q k^T * scale) v for every
+ * (batch, head) in one CTA.  qkv:[B,S,3*heads*dh] (q|k|v thirds, head-major inside), out:[B,S,heads*dh].
+ * S <= 64, dh == 64. */
+int mn_attention(const float* qkv, float* out, int B, int S, int heads, int dh, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Layout conversion at the module boundary (the reference API is NCHW, models/networks.py:42,61,411)
+ * ------------------------------------------------------------------------------------ */
+int mn_nchw_to_nhwc(const float* x, float* y, int N, int C, int H, int W, int y_cs, void* stream);
+int mn_nhwc_to_nchw(const float* x, int x_cs, float* y, int N, int C, int H, int W, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MARCONET_B200_H */

@@ -1,0 +1,34 @@
+// Error reporting, version and device queries of the C ABI (include/marconet_b200.h).
+#include <stdarg.h>
+#include <string.h>
+#include "mn_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void mn_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int mn_num_sms() {
+    static int sms[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (sms[dev] == 0) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        sms[dev] = v;
+    }
+    return sms[dev];
+}
+
+extern "C" const char* mn_last_error(void) { return g_err; }
+extern "C" int mn_version(void) { return 100; }
+extern "C" int mn_device_is_sm100(void) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+    return major == 10;
+}

@@ -1,0 +1,54 @@
+// mn_conv2d_nhwc: argument validation and dispatch between the convolution kernels.
+#include "mn_common.cuh"
+#include "conv_common.cuh"
+
+static int make_geom(const mn_conv_params* p, ConvGeom& g) {
+    MN_REQUIRE(p != nullptr, "mn_conv2d_nhwc: null params");
+    MN_REQUIRE(p->x && p->w && (p->y || p->y2), "mn_conv2d_nhwc: null x/w/y");
+    MN_REQUIRE(p->N > 0 && p->H > 0 && p->W > 0 && p->Cin > 0 && p->Cout > 0, "mn_conv2d_nhwc: non-positive dims");
+    MN_REQUIRE(p->KH > 0 && p->KW > 0 && p->stride_h > 0 && p->stride_w > 0 && p->pad_h >= 0 && p->pad_w >= 0,
+               "mn_conv2d_nhwc: bad kernel/stride/pad");
+    MN_REQUIRE(p->x_cs >= p->Cin, "mn_conv2d_nhwc: x_cs < Cin");
+    g.x = p->x; g.w = p->w; g.y = p->y; g.y2 = p->y2;
+    g.bias = p->bias; g.out_scale = p->out_scale; g.residual = p->residual; g.y2_scale = p->y2_scale;
+    g.valid_w = p->valid_w; g.ws = p->workspace;
+    g.N = p->N; g.H = p->H; g.W = p->W; g.Cin = p->Cin; g.x_cs = p->x_cs;
+    g.KH = p->KH; g.KW = p->KW; g.sh = p->stride_h; g.sw = p->stride_w; g.ph = p->pad_h; g.pw = p->pad_w; g.Cout = p->Cout;
+    g.OH = (p->H + 2 * p->pad_h - p->KH) / p->stride_h + 1;
+    g.OW = (p->W + 2 * p->pad_w - p->KW) / p->stride_w + 1;
+    MN_REQUIRE(g.OH > 0 && g.OW > 0, "mn_conv2d_nhwc: empty output");
+    g.y_cs = p->y_cs; g.y2_cs = p->y2_cs; g.res_cs = p->res_cs; g.res_bcast = p->res_broadcast_n;
+    MN_REQUIRE(!p->y || p->y_cs >= p->Cout, "mn_conv2d_nhwc: y_cs < Cout");
+    MN_REQUIRE(!p->y2 || p->y2_cs >= p->Cout, "mn_conv2d_nhwc: y2_cs < Cout");
+    MN_REQUIRE(!p->residual || p->res_cs >= p->Cout, "mn_conv2d_nhwc: res_cs < Cout");
+    g.os_stride = p->out_scale_stride > 0 ? p->out_scale_stride : p->Cout;
+    g.y2s_stride = p->y2_scale_stride > 0 ? p->y2_scale_stride : p->Cout;
+    g.act = p->act; g.gain = p->act_gain;
+    const int64_t M = (int64_t)p->N * g.OH * g.OW;
+    MN_REQUIRE(M < (1ll << 31) && (int64_t)p->KH * p->KW * p->Cin < (1ll << 31), "mn_conv2d_nhwc: problem too large");
+    g.M = (int)M; g.K = p->KH * p->KW * p->Cin;
+    g.ktiles = g.ktiles_per_split = 0; g.splits = 1;
+    return MN_OK;
+}
+
+extern "C" int64_t mn_conv2d_workspace_bytes(const mn_conv_params* p) {
+    ConvGeom g;
+    if (make_geom(p, g) != MN_OK) return -1;
+    const int splits = mn_conv_simt_plan_splits(g, (int64_t)1 << 60, p->split_k);
+    return splits > 1 ? (int64_t)splits * g.M * g.Cout * 4 : 0;
+}
+
+extern "C" int mn_conv2d_nhwc(const mn_conv_params* p, void* stream) {
+    ConvGeom g;
+    int rc = make_geom(p, g);
+    if (rc != MN_OK) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (p->precision) {
+        case MN_PREC_FP32_SIMT:
+            g.splits = mn_conv_simt_plan_splits(g, p->workspace ? p->workspace_bytes : 0, p->split_k);
+            return mn_conv_simt_launch(g, nullptr, st);
+        default:
+            mn_set_error("mn_conv2d_nhwc: precision mode %d not available in this build", p->precision);
+            return MN_ERR_UNSUPPORTED;
+    }
+}

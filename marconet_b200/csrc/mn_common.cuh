@@ -1,0 +1,60 @@
+// Shared helpers for libmarconet_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/marconet_b200.h"
+
+void mn_set_error(const char* fmt, ...);
+
+#define MN_REQUIRE(cond, ...)                         \
+    do {                                              \
+        if (!(cond)) {                                \
+            mn_set_error(__VA_ARGS__);                \
+            return MN_ERR_INVALID;                    \
+        }                                             \
+    } while (0)
+
+#define MN_CUDA_CHECK(expr)                                                              \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            mn_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return MN_ERR_CUDA;                                                          \
+        }                                                                                \
+    } while (0)
+
+#define MN_LAUNCH_CHECK() MN_CUDA_CHECK(cudaGetLastError())
+
+static inline int mn_cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline int64_t mn_cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ float mn_apply_act(float v, int act) {
+    switch (act) {
+        case MN_ACT_RELU: return fmaxf(v, 0.f);
+        case MN_ACT_LRELU02: return v > 0.f ? v : 0.2f * v;
+        case MN_ACT_TANH: return tanhf(v);
+        case MN_ACT_GELU: return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+        case MN_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+        case MN_ACT_RSQRT_EPS: return rsqrtf(v + 1e-8f);
+        default: return v;
+    }
+}
+
+__device__ __forceinline__ float mn_warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double mn_warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float mn_warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+int mn_num_sms();

@@ -1,0 +1,522 @@
+"""Host-side mirror of the reference's ``models/networks.py`` module API, executed by the
+sm_100a kernels of libmarconet_b200.so through the C ABI (marconet_b200.ops).
+
+Contract: same class names, constructor defaults, ``forward`` signatures,
+return structures and ``state_dict`` keys/shapes as the reference, so the reference's
+``test_sr.py`` / ``test_w.py`` run unmodified with this package providing ``models``.
+
+Design (not a port): the nn.Module tree below only *holds parameters* under the reference's
+key names.  On first use on a CUDA device the parameters are packed once
+(spectral-norm sigma folded, EqualLinear scales folded, 3x3 weights re-laid K-major
+``[ky,kx,Cin][Cout]``, sum-of-squares tables for demodulation, the 17 modulation FCs fused
+into one GEMM) and the forward is a fixed sequence of NHWC kernels:
+  - ModulatedConv2d (reference: per-sample weights + grouped conv, networks.py:281-302) is
+    evaluated with ONE shared weight for all characters:
+        y[n,o] = demod[n,o] * sum_k W[o,k] * (s[n,c(k)] * x[n,k])
+    the style multiply is fused into the producer of x (SelectText / up-sampler / previous
+    conv epilogue), demod + both biases + leaky-relu*sqrt(2) into the conv epilogue;
+  - the per-character Python loops of TSPSRNet.forward (networks.py:425-448, 459-481) run as
+    one ragged batch over all characters of all lines with masked windows.
+There is no CPU / PyTorch fallback: inputs must live on a CUDA device.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..ops import ACT_LRELU02, ACT_NONE, ACT_TANH
+from .resnet import resnet45stride
+from .textvit_arch import TextViT
+
+SQRT2 = math.sqrt(2.0)
+
+
+class _PackedModule(nn.Module):
+    """Parameter container whose packed (kernel-layout) weights are rebuilt lazily."""
+
+    def __init__(self):
+        super().__init__()
+        self._packed = None
+        self._packed_key = None
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
+
+    def _invalidate(self):
+        self._packed = None
+        self._packed_key = None
+
+    def _apply(self, fn, *a, **k):
+        self._invalidate()
+        return super()._apply(fn, *a, **k)
+
+    def _get_packed(self, device):
+        key = (device, tuple(p._version for p in self.parameters()))
+        if self._packed is None or self._packed_key != key:
+            with torch.no_grad():
+                self._packed = self._pack(device)
+            self._packed_key = key
+        return self._packed
+
+    @staticmethod
+    def _need_cuda(t, what):
+        if not t.is_cuda:
+            raise RuntimeError(f"marconet_b200.{what}: input is on {t.device}; this implementation runs only on "
+                               f"CUDA (sm_100a) devices and has no CPU fallback")
+
+
+def _pack_conv_weight(w):
+    """[Cout, Cin, KH, KW] -> K-major [KH*KW*Cin, Cout] fp32 contiguous."""
+    cout, cin, kh, kw = w.shape
+    return w.permute(2, 3, 1, 0).reshape(kh * kw * cin, cout).contiguous()
+
+
+# =========================================================================================
+# 1) TextContextEncoderV2  (reference models/networks.py:27-45)
+# =========================================================================================
+class TextContextEncoderV2(_PackedModule):
+    """LR line -> (char logits [B,64,6736], boxes [B,32], font style w [B,512])."""
+
+    def __init__(self, dim=512, num_classes=6736):
+        super().__init__()
+        self.resnet = resnet45stride()
+        self.transformer = TextViT(num_classes=num_classes, dim=512, max_length=16)
+
+    def _pack(self, device):
+        return dict(resnet=self.resnet.pack(), vit=self.transformer.pack())
+
+    @torch.no_grad()
+    def forward(self, lq):
+        self._need_cuda(lq, "TextContextEncoderV2")
+        pk = self._get_packed(lq.device)
+        x = ops.nchw_to_nhwc(lq.float())
+        feat = self.resnet.run(pk["resnet"], x)
+        return self.transformer.run(pk["vit"], feat)
+
+
+# =========================================================================================
+# 2) TSPGAN  (reference models/networks.py:51-321)
+# =========================================================================================
+class PixelNorm(nn.Module):
+    def forward(self, input):
+        return ops.pixelnorm(input)
+
+
+class EqualLinear(nn.Module):
+    """Parameter holder for the equalised-lr linear layer (reference networks.py:173-198)."""
+
+    def __init__(self, in_channels, out_channels, bias=True, bias_init_val=0, lr_mul=1, activation=None):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.lr_mul, self.activation = lr_mul, activation
+        self.scale = (1 / math.sqrt(in_channels)) * lr_mul
+        self.weight = nn.Parameter(torch.randn(out_channels, in_channels).div_(lr_mul))
+        if bias:
+            self.bias = nn.Parameter(torch.zeros(out_channels).fill_(bias_init_val))
+        else:
+            self.register_parameter("bias", None)
+
+    def packed(self):
+        """([in, out] weight with the equalised-lr scale folded, bias * lr_mul)."""
+        w = (self.weight * self.scale).t().contiguous()
+        b = None if self.bias is None else (self.bias * self.lr_mul).contiguous()
+        return w, b
+
+    @torch.no_grad()
+    def forward(self, x):
+        w, b = self.packed()
+        if self.activation == "fused_lrelu":
+            return ops.linear(x.contiguous(), w, b, act=ACT_LRELU02, gain=SQRT2)
+        return ops.linear(x.contiguous(), w, b)
+
+
+class SelectText(nn.Module):
+    def __init__(self, class_num, channel, size=4):
+        super().__init__()
+        self.size = size
+        self.TextEmbeddings = nn.Parameter(torch.randn(class_num, channel, 1, 1))
+
+
+class FusedLeakyReLU(nn.Module):
+    """Holds the ``activate.bias`` parameter of the third-party basicsr FusedLeakyReLU."""
+
+    def __init__(self, channel):
+        super().__init__()
+        self.bias = nn.Parameter(torch.zeros(channel))
+
+
+class ModulatedConv2d(nn.Module):
+    def __init__(self, in_channel, out_channel, kernel_size, style_dim, demodulate=True, upsample=False,
+                 downsample=False, blur_kernel=[1, 3, 3, 1]):
+        super().__init__()
+        self.eps = 1e-8
+        self.kernel_size, self.in_channel, self.out_channel = kernel_size, in_channel, out_channel
+        self.upsample, self.downsample, self.demodulate = upsample, downsample, demodulate
+        self.scale = 1 / math.sqrt(in_channel * kernel_size ** 2)
+        self.padding = kernel_size // 2
+        self.weight = nn.Parameter(torch.randn(1, out_channel, in_channel, kernel_size, kernel_size))
+        self.modulation = EqualLinear(style_dim, in_channel, bias=True, bias_init_val=1, lr_mul=1, activation=None)
+
+
+class StyledConv(nn.Module):
+    def __init__(self, in_channel, out_channel, kernel_size, style_dim, upsample=False, blur_kernel=[1, 3, 3, 1],
+                 demodulate=True):
+        super().__init__()
+        self.conv = ModulatedConv2d(in_channel, out_channel, kernel_size, style_dim, upsample=upsample,
+                                    blur_kernel=blur_kernel, demodulate=demodulate)
+        self.bias = nn.Parameter(torch.zeros(1, out_channel, 1, 1))
+        self.activate = FusedLeakyReLU(out_channel)
+
+
+class ToRGB(nn.Module):
+    def __init__(self, in_channel, style_dim, upsample=True, blur_kernel=[1, 3, 3, 1]):
+        super().__init__()
+        self.upsample = upsample
+        self.conv = ModulatedConv2d(in_channel, 3, 1, style_dim, demodulate=False)
+        self.bias = nn.Parameter(torch.zeros(1, 3, 1, 1))
+
+
+class TextGenerator(_PackedModule):
+    """font style w + character labels -> (128-px structure image, 64x64 prior, 32x32 prior)."""
+
+    def __init__(self, size, style_dim, n_mlp, class_num, channel_multiplier=1, blur_kernel=[1, 3, 3, 1], lr_mlp=0.01):
+        super().__init__()
+        self.size, self.n_mlp, self.style_dim = size, n_mlp, style_dim
+        self.style_mlp = nn.Sequential(PixelNorm(), *[
+            EqualLinear(style_dim, style_dim, bias=True, bias_init_val=0, lr_mul=lr_mlp, activation="fused_lrelu")
+            for _ in range(n_mlp)])
+        m = channel_multiplier
+        self.channels = {4: 512, 8: 512, 16: 512, 32: 512, 64: 256 * m, 128: 128 * m, 256: 64 * m, 512: 32 * m, 1024: 16 * m}
+        self.input_text = SelectText(class_num, self.channels[4])
+        self.conv1 = StyledConv(self.channels[4], self.channels[4], 3, style_dim, blur_kernel=blur_kernel)
+        self.to_rgb1 = ToRGB(self.channels[4], style_dim, upsample=False)
+        self.log_size = int(math.log(size, 2))
+        self.convs, self.upsamples, self.to_rgbs = nn.ModuleList(), nn.ModuleList(), nn.ModuleList()
+        cin = self.channels[4]
+        for i in range(3, self.log_size + 1):
+            cout = self.channels[2 ** i]
+            self.convs.append(StyledConv(cin, cout, 3, style_dim, upsample=True, blur_kernel=blur_kernel))
+            self.convs.append(StyledConv(cout, cout, 3, style_dim, blur_kernel=blur_kernel))
+            self.to_rgbs.append(ToRGB(cout, style_dim))
+            cin = cout
+        self.n_latent = self.log_size * 2 - 2
+
+    # ---- pack -----------------------------------------------------------------------------
+    def _pack(self, device):
+        pk = {}
+        pk["mlp"] = [m.packed() for m in list(self.style_mlp)[1:]]
+        styled = [self.conv1] + list(self.convs)
+        rgbs = [self.to_rgb1] + list(self.to_rgbs)
+        # one GEMM for all 17 modulation FCs: columns [conv1 | convs.* | to_rgb1 | to_rgbs.*]
+        mods = [m.conv.modulation for m in styled] + [m.conv.modulation for m in rgbs]
+        ws, bs, offs, off = [], [], [], 0
+        for mod in mods:
+            w, b = mod.packed()
+            ws.append(w); bs.append(b); offs.append((off, w.shape[1])); off += w.shape[1]
+        pk["mod_w"] = torch.cat(ws, dim=1).contiguous()
+        pk["mod_b"] = torch.cat(bs).contiguous()
+        pk["mod_total"] = off
+        pk["styled"] = []
+        for i, m in enumerate(styled):
+            w = m.conv.weight[0] * m.conv.scale                      # [Cout, Cin, 3, 3]  (networks.py:284)
+            pk["styled"].append(dict(
+                w=_pack_conv_weight(w), wsq=w.pow(2).sum([2, 3]).t().contiguous(),   # [Cin, Cout]
+                bias=(m.bias.reshape(-1) + m.activate.bias).contiguous(),
+                off=offs[i], up=m.conv.upsample, cout=w.shape[0]))
+        pk["rgb"] = []
+        for i, m in enumerate(rgbs):
+            w = (m.conv.weight[0, :, :, 0, 0] * m.conv.scale).contiguous()          # [3, Cin]
+            pk["rgb"].append(dict(w=w, bias=m.bias.reshape(-1).contiguous(), off=offs[len(styled) + i]))
+        pk["emb"] = self.input_text.TextEmbeddings[:, :, 0, 0].contiguous()
+        return pk
+
+    # ---- forward --------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, styles, labels, noise=None):
+        self._need_cuda(styles, "TSPGAN")
+        dev = styles.device
+        pk = self._get_packed(dev)
+        if labels.dim() != 2:
+            raise RuntimeError("labels must be [N, L]")
+        n, l = labels.shape
+        if styles.shape[0] != n:
+            raise RuntimeError("styles and labels disagree on the number of characters")
+        lab_host = labels.detach().to("cpu", torch.int64)
+        if n * l > 0 and (int(lab_host.min()) < 0 or int(lab_host.max()) >= pk["emb"].shape[0]):
+            raise IndexError(f"character label out of range [0, {pk['emb'].shape[0]}) "
+                             f"(reference: empty embedding slice, networks.py:211)")
+        lab_dev = labels.to(dev, torch.int64).contiguous().reshape(-1) if labels.is_cuda else \
+            lab_host.reshape(-1).to(dev, non_blocking=False)
+
+        z = ops.pixelnorm(styles.float().contiguous())
+        for w, b in pk["mlp"]:
+            z = ops.linear(z, w, b, act=ACT_LRELU02, gain=SQRT2)
+        s_all = ops.linear(z, pk["mod_w"], pk["mod_b"])              # [N, 7168]
+
+        def s_of(entry):
+            o, c = entry["off"]
+            return s_all[:, o:o + c]
+
+        st = pk["styled"]
+        demods = [ops.demod(s_of(e), e["wsq"]) for e in st]
+
+        def styled(i, x, want_y, next_i=None):
+            e = st[i]
+            y2s = None if next_i is None else s_of(st[next_i])
+            return ops.conv2d(x, e["w"], 3, 3, pad=(1, 1), bias=e["bias"], out_scale=demods[i], act=ACT_LRELU02,
+                              gain=SQRT2, want_y=want_y, out2=(True if next_i is not None else None), y2_scale=y2s)
+
+        x = ops.select_text(pk["emb"], lab_dev, s_of(st[0]), n, l)   # embedding * style(conv1)
+        y = styled(0, x, True)
+        skip = ops.torgb(y, s_of(pk["rgb"][0]), pk["rgb"][0]["w"], pk["rgb"][0]["bias"], None)
+        taps = {}
+        for j in range(len(self.to_rgbs)):
+            ia, ib = 1 + 2 * j, 2 + 2 * j
+            xu = ops.resample_modulate(y, s_of(st[ia]), up=True)     # bilinear x2 of the un-modulated map, then style
+            xm = styled(ia, xu, False, next_i=ib)                    # only the pre-modulated operand of conv b is kept
+            y = styled(ib, xm, True)
+            r = pk["rgb"][1 + j]
+            skip = ops.torgb(y, s_of(r), r["w"], r["bias"], skip)
+            taps[y.shape[1]] = y
+        return ops.as_nchw_view(skip), ops.as_nchw_view(taps[64]), ops.as_nchw_view(taps[32])
+
+
+class TSPGAN(nn.Module):
+    def __init__(self, out_size=128, num_style_feat=512, class_num=6736, num_mlp=8):
+        super().__init__()
+        self.TextGenerator = TextGenerator(size=out_size, style_dim=num_style_feat, n_mlp=num_mlp, class_num=class_num)
+
+    def forward(self, styles, labels, noise):
+        return self.TextGenerator(styles, labels, noise)
+
+
+# =========================================================================================
+# 3) TSPSRNet  (reference models/networks.py:328-533)
+# =========================================================================================
+class _SNConv(nn.Module):
+    """Spectral-norm 3x3 conv parameter holder with torch.nn.utils.spectral_norm's state_dict keys
+    (bias, weight_orig, weight_u, weight_v).  sigma is folded into the weight once at pack time
+    (eval branch of spectral_norm: W / (u . W_mat v))."""
+
+    def __init__(self, cin, cout, stride=1):
+        super().__init__()
+        self.in_channels, self.out_channels, self.stride = cin, cout, stride
+        conv = nn.Conv2d(cin, cout, 3, stride, 1)
+        self.bias = nn.Parameter(conv.bias.detach().clone())
+        self.weight_orig = nn.Parameter(conv.weight.detach().clone())
+        wm = self.weight_orig.detach().flatten(1)
+        u = nn.functional.normalize(torch.randn(cout), dim=0, eps=1e-12)
+        v = nn.functional.normalize(torch.randn(cin * 9), dim=0, eps=1e-12)
+        for _ in range(8):   # settle sigma so that a default-initialised net is finite in eval mode
+            v = nn.functional.normalize(torch.mv(wm.t(), u), dim=0, eps=1e-12)
+            u = nn.functional.normalize(torch.mv(wm, v), dim=0, eps=1e-12)
+        self.register_buffer("weight_u", u)
+        self.register_buffer("weight_v", v)
+
+    def packed(self):
+        w = self.weight_orig
+        sigma = torch.dot(self.weight_u, torch.mv(w.flatten(1), self.weight_v))
+        return _pack_conv_weight(w / sigma), self.bias.contiguous()
+
+
+class _Slot(nn.Module):
+    """Parameter-free placeholder keeping nn.Sequential indices aligned with the reference
+    (LeakyReLU / Upsample / Tanh positions)."""
+
+    def __init__(self, what):
+        super().__init__()
+        self.what = what
+
+    def extra_repr(self):
+        return self.what
+
+
+def GroupNorm(in_channels):
+    assert in_channels % 32 == 0
+    return nn.GroupNorm(num_groups=in_channels // 32, num_channels=in_channels, eps=1e-6, affine=True)
+
+
+class ResTextBlockV2(nn.Module):
+    def __init__(self, in_channels, out_channels=None):
+        super().__init__()
+        self.in_channels = in_channels
+        self.out_channels = in_channels if out_channels is None else out_channels
+        self.norm1 = GroupNorm(in_channels)
+        self.conv1 = _SNConv(in_channels, self.out_channels)
+        self.norm2 = GroupNorm(self.out_channels)
+        self.conv2 = _SNConv(self.out_channels, self.out_channels)
+        if self.in_channels != self.out_channels:
+            self.conv_out = nn.Conv2d(in_channels, self.out_channels, kernel_size=1, stride=1, padding=0)
+
+    def packed(self):
+        d = dict(n1=(self.norm1.weight.contiguous(), self.norm1.bias.contiguous()), c1=self.conv1.packed(),
+                 n2=(self.norm2.weight.contiguous(), self.norm2.bias.contiguous()), c2=self.conv2.packed(), co=None)
+        if self.in_channels != self.out_channels:
+            d["co"] = (_pack_conv_weight(self.conv_out.weight), self.conv_out.bias.contiguous())
+        return d
+
+
+def _res_block(pk, x, valid_w=None):
+    """GN -> swish -> conv -> GN -> swish -> conv (+ 1x1 skip), reference networks.py:506-516."""
+    h = ops.groupnorm_swish(x, *pk["n1"], valid_w=valid_w)
+    h = ops.conv2d(h, pk["c1"][0], 3, 3, pad=(1, 1), bias=pk["c1"][1], valid_w=valid_w)
+    h = ops.groupnorm_swish(h, *pk["n2"], valid_w=valid_w)
+    skip = x if pk["co"] is None else ops.conv2d(x, pk["co"][0], 1, 1, bias=pk["co"][1], valid_w=valid_w)
+    return ops.conv2d(h, pk["c2"][0], 3, 3, pad=(1, 1), bias=pk["c2"][1], residual=skip, valid_w=valid_w)
+
+
+def _two(pk, x, valid_w=None):
+    """SN-conv -> LeakyReLU(0.2) -> SN-conv."""
+    t = ops.conv2d(x, pk[0][0], 3, 3, pad=(1, 1), bias=pk[0][1], act=ACT_LRELU02, valid_w=valid_w)
+    return ops.conv2d(t, pk[1][0], 3, 3, pad=(1, 1), bias=pk[1][1], valid_w=valid_w)
+
+
+def char_windows(locs_host, counts, width, half):
+    """Bit-exact restatement of the window integers of reference networks.py:426-441 / :460-474.
+
+    ``locs_host`` is a CPU fp32 tensor [B, 2*n]; the centre is ``(locs[b][2c] * W).int()`` (fp32
+    multiply, truncation).  Returns (windows [(line,x1,x2,y1)], valid widths, owner[b][x]) with
+    "last character in program order wins" ownership (networks.py:448,481).
+    """
+    wins, valid = [], []
+    owner = [[-1] * width for _ in counts]
+    i = 0
+    for b, n in enumerate(counts):
+        for c in range(n):
+            center = int((locs_host[b][2 * c] * width).int())
+            x1 = 0 if center < half else center - half
+            x2 = width if center + half > width else center + half
+            wv = x2 - x1
+            if wv <= 0 or x1 >= width:
+                raise RuntimeError(f"character {c} of line {b}: empty window (centre {center}); the reference "
+                                   f"fails on the empty slice at networks.py:443")
+            y1 = half - int(math.trunc(wv / 2))
+            wins.append((b, x1, x2, y1))
+            valid.append(wv)
+            for x in range(x1, x2):
+                owner[b][x] = i
+            i += 1
+    return wins, valid, owner
+
+
+class TSPSRNet(_PackedModule):
+    """LR line + per-character structure priors + boxes -> SR line [B,3,128,2048]."""
+
+    def __init__(self, in_channel=3, dim_channel=256):
+        super().__init__()
+        d = dim_channel
+        act, up = (lambda: _Slot("LeakyReLU(0.2)")), (lambda: _Slot("Upsample(x2, bilinear)"))
+        self.conv_first_32 = nn.Sequential(_SNConv(in_channel, d // 4), act())
+        self.conv_first_16 = nn.Sequential(_SNConv(d // 4, d // 2, 2), act())
+        self.conv_first_8 = nn.Sequential(_SNConv(d // 2, d, 2), act(), _SNConv(d, d))
+        self.conv_body_16 = nn.Sequential(_SNConv(d + d // 2, d), act(), _SNConv(d, d))
+        self.conv_body_32 = nn.Sequential(_SNConv(d + d // 4, d), act(), _SNConv(d, d))
+        self.conv_up = nn.Sequential(up(), _SNConv(d, d), act(), ResTextBlockV2(d, d), _SNConv(d, d))
+        self.conv_final = nn.Sequential(_SNConv(d, d // 2), act(), up(), _SNConv(d // 2, d // 4), act(),
+                                        ResTextBlockV2(d // 4, d // 4), _SNConv(d // 4, 3), _Slot("Tanh"))
+        self.conv_32_scale = nn.Sequential(_SNConv(d, d), act(), _SNConv(d, d))
+        self.conv_32_shift = nn.Sequential(_SNConv(d, d), act(), _SNConv(d, d))
+        self.conv_32_fuse = nn.Sequential(ResTextBlockV2(2 * d, d))
+        self.conv_32_to256 = nn.Sequential(_SNConv(512, d), act(), _SNConv(d, d))
+        self.conv_64_scale = nn.Sequential(_SNConv(d, d), act(), _SNConv(d, d))
+        self.conv_64_shift = nn.Sequential(_SNConv(d, d), act(), _SNConv(d, d))
+        self.conv_64_fuse = nn.Sequential(ResTextBlockV2(2 * d, d))
+        self.dim = d
+
+    def _pack(self, device):
+        pk = {}
+        for name in ("conv_first_8", "conv_body_16", "conv_body_32", "conv_32_scale", "conv_32_shift", "conv_32_to256",
+                     "conv_64_scale", "conv_64_shift"):
+            seq = getattr(self, name)
+            pk[name] = (seq[0].packed(), seq[2].packed())
+        pk["first_32"] = self.conv_first_32[0].packed()
+        pk["first_16"] = self.conv_first_16[0].packed()
+        pk["up_1"] = self.conv_up[1].packed()
+        pk["up_res"] = self.conv_up[3].packed()
+        pk["up_4"] = self.conv_up[4].packed()
+        pk["fin_0"] = self.conv_final[0].packed()
+        pk["fin_3"] = self.conv_final[3].packed()
+        pk["fin_res"] = self.conv_final[5].packed()
+        pk["fin_6"] = self.conv_final[6].packed()
+        pk["fuse32"] = self.conv_32_fuse[0].packed()
+        pk["fuse64"] = self.conv_64_fuse[0].packed()
+        return pk
+
+    def _fuse(self, pk, lvl, feat, prior, locs_host, counts, half):
+        """Per-character prior fusion of one level as ONE ragged batch (reference loops :425-448/:459-481)."""
+        dev = feat.device
+        b, h, w, c = feat.shape
+        wins, valid, owner = char_windows(locs_host, counts, w, half)
+        nc = len(wins)
+        if nc == 0:
+            return feat
+        wp = 2 * half
+        win_dev = torch.tensor(wins, dtype=torch.int32).to(dev)
+        valid_dev = torch.tensor(valid, dtype=torch.int32).to(dev)
+        owner_dev = torch.tensor(owner, dtype=torch.int32).to(dev)
+        vw = valid_dev if min(valid) < wp else None       # full-width windows need no masking
+        fin = ops.adain_concat(prior, feat, win_dev, nc, wp)                         # [Nc,H,wp,2C]
+        fuse = _res_block(pk[f"fuse{lvl}"], fin, vw)
+        scale = _two(pk[f"conv_{lvl}_scale"], fuse, vw)
+        shift = _two(pk[f"conv_{lvl}_shift"], fuse, vw)
+        return ops.window_scatter(feat, scale, shift, owner_dev, win_dev, wp)
+
+    @staticmethod
+    def _gather_priors(priors, channels, size):
+        views = []
+        for p in priors:
+            if p.dim() != 4 or p.shape[1] != channels or p.shape[2] != size or p.shape[3] != size:
+                raise RuntimeError(f"prior has shape {tuple(p.shape)}, expected [n,{channels},{size},{size}]")
+            views.append(ops.as_nhwc(p.float()))
+        return views[0] if len(views) == 1 else torch.cat(views, dim=0)
+
+    @torch.no_grad()
+    def forward(self, lq, priors64, priors32, locs):
+        self._need_cuda(lq, "TSPSRNet")
+        dev = lq.device
+        pk = self._get_packed(dev)
+        d = self.dim
+        bsz = lq.shape[0]
+        if len(priors64) != len(priors32):
+            raise RuntimeError("priors64 and priors32 must have one entry per line")
+        counts = [int(p.shape[0]) for p in priors32] + [0] * (bsz - len(priors32))
+        if [int(p.shape[0]) for p in priors64] != counts[:len(priors64)]:
+            raise RuntimeError("priors64 / priors32 disagree on the number of characters")
+        locs_host = locs.detach().to("cpu", torch.float32)
+
+        x = ops.nchw_to_nhwc(lq.float())
+        h, w = x.shape[1], x.shape[2]
+        cat32 = torch.empty((bsz, h, w, d + d // 4), dtype=torch.float32, device=dev)        # [up(sq_f_16) | lq_f_32]
+        cat16 = torch.empty((bsz, h // 2, w // 2, d + d // 2), dtype=torch.float32, device=dev)  # [up(lq_f_8) | lq_f_16]
+        f32v, f16v = cat32[..., d:], cat16[..., d:]
+        ops.conv2d(x, pk["first_32"][0], 3, 3, pad=(1, 1), bias=pk["first_32"][1], act=ACT_LRELU02, out=f32v)
+        ops.conv2d(f32v, pk["first_16"][0], 3, 3, stride=(2, 2), pad=(1, 1), bias=pk["first_16"][1], act=ACT_LRELU02, out=f16v)
+        p8 = pk["conv_first_8"]
+        t = ops.conv2d(f16v, p8[0][0], 3, 3, stride=(2, 2), pad=(1, 1), bias=p8[0][1], act=ACT_LRELU02)
+        f8 = ops.conv2d(t, p8[1][0], 3, 3, pad=(1, 1), bias=p8[1][1])
+        ops.resample_modulate(f8, None, up=True, out=cat16[..., :d])
+        s16 = _two(pk["conv_body_16"], cat16)
+        ops.resample_modulate(s16, None, up=True, out=cat32[..., :d])
+        s32 = _two(pk["conv_body_32"], cat32)
+
+        if sum(counts) > 0:
+            p32 = _two(pk["conv_32_to256"], self._gather_priors(priors32, 512, 32))
+            s32 = self._fuse(pk, 32, s32, p32, locs_host, counts, 16)
+
+        u = ops.resample_modulate(s32, None, up=True)
+        x = ops.conv2d(u, pk["up_1"][0], 3, 3, pad=(1, 1), bias=pk["up_1"][1], act=ACT_LRELU02)
+        x = _res_block(pk["up_res"], x)
+        s64 = ops.conv2d(x, pk["up_4"][0], 3, 3, pad=(1, 1), bias=pk["up_4"][1])
+
+        if sum(counts) > 0:
+            s64 = self._fuse(pk, 64, s64, self._gather_priors(priors64, d, 64), locs_host, counts, 32)
+
+        x = ops.conv2d(s64, pk["fin_0"][0], 3, 3, pad=(1, 1), bias=pk["fin_0"][1], act=ACT_LRELU02)
+        u = ops.resample_modulate(x, None, up=True)
+        x = ops.conv2d(u, pk["fin_3"][0], 3, 3, pad=(1, 1), bias=pk["fin_3"][1], act=ACT_LRELU02)
+        x = _res_block(pk["fin_res"], x)
+        out = ops.conv2d(x, pk["fin_6"][0], 3, 3, pad=(1, 1), bias=pk["fin_6"][1], act=ACT_TANH)
+        return ops.as_nchw_view(out)
+
+
+def swish(x):
+    raise RuntimeError("swish is fused into mn_groupnorm_swish in marconet_b200 (no standalone CPU op)")

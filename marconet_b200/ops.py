@@ -1,0 +1,282 @@
+"""Torch-tensor wrappers over the C ABI (include/marconet_b200.h).
+
+PyTorch is plumbing here: it owns device memory and the current CUDA stream; every
+computation below is a kernel from libmarconet_b200.so.  Activations are NHWC fp32 views
+``[N, H, W, C]`` with ``stride(-1) == 1`` whose pixel stride (``cs``) may exceed C (channel
+slices of a concatenation buffer).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_GELU, ACT_LRELU02, ACT_NONE, ACT_RELU, ACT_RSQRT_EPS, ACT_SIGMOID, ACT_TANH,  # noqa: F401
+                   PREC_BF16X3_TC, PREC_F16X1_TC, PREC_F16X3_TC, PREC_FP32_SIMT, ConvParams, Window)
+
+_WS = {}
+_WS_BYTES = 96 << 20
+_DEFAULT_PRECISION = PREC_FP32_SIMT
+LAUNCHES = 0   # number of C-ABI kernel-launching calls issued (bench.py reports it)
+
+
+def set_default_precision(p):
+    global _DEFAULT_PRECISION
+    _DEFAULT_PRECISION = int(p)
+
+
+def default_precision():
+    return _DEFAULT_PRECISION
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _require_cuda(t, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"marconet_b200: {name} must be a CUDA tensor (there is no CPU path)")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"marconet_b200: {name} must be float32, got {t.dtype}")
+
+
+def nhwc_info(t, name="tensor"):
+    """(N, H, W, C, cs) of an NHWC view; verifies the stride pattern."""
+    _require_cuda(t, name)
+    if t.dim() != 4:
+        raise RuntimeError(f"{name}: expected 4-D NHWC view, got {tuple(t.shape)}")
+    n, h, w, c = t.shape
+    sn, sh, sw, sc = t.stride()
+    cs = sw if w > 1 else (sh if h > 1 else (sn if n > 1 else c))
+    ok = (sc == 1 or c == 1) and (w == 1 or sw == cs) and (h == 1 or sh == w * cs) and (n == 1 or sn == h * w * cs)
+    if not ok:
+        raise RuntimeError(f"{name}: not a dense NHWC view (shape {tuple(t.shape)}, strides {t.stride()})")
+    return n, h, w, c, cs
+
+
+def workspace(device):
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    ws = _WS.get(key)
+    if ws is None:
+        ws = torch.empty(_WS_BYTES // 4, dtype=torch.float32, device=device)
+        _WS[key] = ws
+    return ws
+
+
+def conv2d(x, w, kh, kw, stride=(1, 1), pad=(0, 0), bias=None, out_scale=None, residual=None,
+           res_broadcast=False, act=ACT_NONE, gain=1.0, out=None, out2=None, y2_scale=None,
+           valid_w=None, precision=None, want_y=True, split_k=0):
+    """mn_conv2d_nhwc.  ``w`` is the packed [KH*KW*Cin, Cout] matrix.  Returns y (or (y, y2))."""
+    global LAUNCHES
+    lib = _lib.load()
+    n, h, wd, cin, x_cs = nhwc_info(x, "x")
+    cout = w.shape[1]
+    if w.shape[0] != kh * kw * cin:
+        raise RuntimeError(f"conv2d: packed weight has {w.shape[0]} rows, expected {kh * kw * cin}")
+    oh = (h + 2 * pad[0] - kh) // stride[0] + 1
+    ow = (wd + 2 * pad[1] - kw) // stride[1] + 1
+    p = ConvParams()
+    p.x = x.data_ptr(); p.N = n; p.H = h; p.W = wd; p.Cin = cin; p.x_cs = x_cs
+    p.w = w.data_ptr(); p.KH = kh; p.KW = kw; p.stride_h, p.stride_w = stride; p.pad_h, p.pad_w = pad; p.Cout = cout
+    y = None
+    if want_y:
+        y = out if out is not None else torch.empty((n, oh, ow, cout), dtype=torch.float32, device=x.device)
+        yn, yh, yw, yc, y_cs = nhwc_info(y, "out")
+        if (yn, yh, yw, yc) != (n, oh, ow, cout):
+            raise RuntimeError(f"conv2d: out has shape {tuple(y.shape)}, expected {(n, oh, ow, cout)}")
+        p.y = y.data_ptr(); p.y_cs = y_cs
+    y2 = None
+    if out2 is not None:
+        y2 = out2 if isinstance(out2, torch.Tensor) else torch.empty((n, oh, ow, cout), dtype=torch.float32, device=x.device)
+        _, _, _, _, y2_cs = nhwc_info(y2, "out2")
+        p.y2 = y2.data_ptr(); p.y2_cs = y2_cs
+        if y2_scale is not None:
+            p.y2_scale = y2_scale.data_ptr(); p.y2_scale_stride = y2_scale.stride(0)
+    if bias is not None:
+        p.bias = bias.data_ptr()
+    if out_scale is not None:
+        p.out_scale = out_scale.data_ptr(); p.out_scale_stride = out_scale.stride(0)
+    if residual is not None:
+        rinfo = nhwc_info(residual, "residual")
+        p.residual = residual.data_ptr(); p.res_cs = rinfo[4]; p.res_broadcast_n = 1 if res_broadcast else 0
+    p.act = act; p.act_gain = gain
+    if valid_w is not None:
+        p.valid_w = valid_w.data_ptr()
+    ws = workspace(x.device)
+    p.workspace = ws.data_ptr(); p.workspace_bytes = ws.numel() * 4
+    p.split_k = split_k
+    p.precision = _DEFAULT_PRECISION if precision is None else precision
+    _lib.check(lib.mn_conv2d_nhwc(ctypes.byref(p), _stream()), "mn_conv2d_nhwc")
+    LAUNCHES += 1
+    if y2 is not None:
+        return (y, y2) if want_y else y2
+    return y
+
+
+def linear(x2d, w, bias=None, act=ACT_NONE, gain=1.0, residual=None, out=None, precision=None):
+    """nn.Linear as a 1x1 conv on [M,1,1,K]; ``w`` packed [K, Cout]; x2d: [M, K] contiguous."""
+    m, k = x2d.shape
+    res = None if residual is None else residual.reshape(m, 1, 1, -1)
+    o = None if out is None else out.reshape(m, 1, 1, -1)
+    y = conv2d(x2d.reshape(m, 1, 1, k), w, 1, 1, bias=bias, act=act, gain=gain, residual=res, out=o, precision=precision)
+    return y.reshape(m, -1)
+
+
+def pixelnorm(x):
+    global LAUNCHES
+    _require_cuda(x, "x")
+    y = torch.empty_like(x)
+    _lib.check(_lib.load().mn_pixelnorm(_ptr(x), _ptr(y), x.shape[0], x.shape[1], _stream()), "mn_pixelnorm")
+    LAUNCHES += 1
+    return y
+
+
+def select_text(emb, labels_dev, s, n, l):
+    """emb: [classes, C]; labels_dev: int64 [n*l] on device; s: [n, C] view (row stride s.stride(0)) or None."""
+    global LAUNCHES
+    c = emb.shape[1]
+    out = torch.empty((n, 4, 4 * l, c), dtype=torch.float32, device=emb.device)
+    _lib.check(_lib.load().mn_select_text(_ptr(emb), _ptr(labels_dev), _ptr(s), 0 if s is None else s.stride(0),
+                                          _ptr(out), n, l, c, _stream()), "mn_select_text")
+    LAUNCHES += 1
+    return out
+
+
+def demod(s, wsq):
+    """s: [N, Cin] view; wsq: [Cin, Cout] -> [N, Cout]."""
+    global LAUNCHES
+    n, cin = s.shape
+    cout = wsq.shape[1]
+    out = torch.empty((n, cout), dtype=torch.float32, device=s.device)
+    _lib.check(_lib.load().mn_demod(_ptr(s), s.stride(0), _ptr(wsq), _ptr(out), n, cin, cout, _stream()), "mn_demod")
+    LAUNCHES += 1
+    return out
+
+
+def resample_modulate(x, s=None, up=False, out=None):
+    global LAUNCHES
+    n, h, w, c, x_cs = nhwc_info(x, "x")
+    oh, ow = (2 * h, 2 * w) if up else (h, w)
+    y = out if out is not None else torch.empty((n, oh, ow, c), dtype=torch.float32, device=x.device)
+    _, _, _, _, y_cs = nhwc_info(y, "out")
+    _lib.check(_lib.load().mn_resample_modulate(_ptr(x), x_cs, _ptr(y), y_cs, _ptr(s), 0 if s is None else s.stride(0),
+                                                n, h, w, c, 1 if up else 0, _stream()), "mn_resample_modulate")
+    LAUNCHES += 1
+    return y
+
+
+def torgb(x, s, w, bias, skip=None):
+    global LAUNCHES
+    n, h, wd, c, x_cs = nhwc_info(x, "x")
+    out = torch.empty((n, h, wd, 3), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().mn_torgb(_ptr(x), x_cs, _ptr(s), s.stride(0), _ptr(w), _ptr(bias), _ptr(skip), _ptr(out),
+                                    n, h, wd, c, _stream()), "mn_torgb")
+    LAUNCHES += 1
+    return out
+
+
+def groupnorm_swish(x, gamma, beta, cpg=32, eps=1e-6, swish=True, valid_w=None, out=None):
+    global LAUNCHES
+    n, h, w, c, x_cs = nhwc_info(x, "x")
+    y = out if out is not None else torch.empty((n, h, w, c), dtype=torch.float32, device=x.device)
+    _, _, _, _, y_cs = nhwc_info(y, "out")
+    stats = torch.empty((n * (c // cpg) * 2,), dtype=torch.float64, device=x.device)
+    _lib.check(_lib.load().mn_groupnorm_swish(_ptr(x), x_cs, _ptr(y), y_cs, _ptr(gamma), _ptr(beta), n, h, w, c, cpg,
+                                              eps, 1 if swish else 0, _ptr(valid_w), _ptr(stats), _stream()),
+               "mn_groupnorm_swish")
+    LAUNCHES += 3
+    return y
+
+
+def adain_concat(prior, feat, win_dev, nc, wp):
+    global LAUNCHES
+    pn, h, pw, c, p_cs = nhwc_info(prior, "prior")
+    b, fh, w, fc, f_cs = nhwc_info(feat, "feat")
+    if pn != nc or pw != wp or fh != h or fc != c:
+        raise RuntimeError("adain_concat: shape mismatch")
+    out = torch.empty((nc, h, wp, 2 * c), dtype=torch.float32, device=feat.device)
+    _lib.check(_lib.load().mn_adain_concat(_ptr(prior), p_cs, _ptr(feat), f_cs, _ptr(win_dev), _ptr(out), nc, h, wp, w, c,
+                                           _stream()), "mn_adain_concat")
+    LAUNCHES += 1
+    return out
+
+
+def window_scatter(feat, scale, shift, owner_dev, win_dev, wp, out=None):
+    global LAUNCHES
+    b, h, w, c, f_cs = nhwc_info(feat, "feat")
+    y = out if out is not None else torch.empty((b, h, w, c), dtype=torch.float32, device=feat.device)
+    _, _, _, _, y_cs = nhwc_info(y, "out")
+    _lib.check(_lib.load().mn_window_scatter(_ptr(feat), f_cs, _ptr(scale), _ptr(shift), _ptr(owner_dev), _ptr(win_dev),
+                                             _ptr(y), y_cs, b, h, w, wp, c, _stream()), "mn_window_scatter")
+    LAUNCHES += 1
+    return y
+
+
+def layernorm(x2d, gamma, beta, eps=1e-5):
+    global LAUNCHES
+    _require_cuda(x2d, "x")
+    rows, dim = x2d.shape
+    y = torch.empty_like(x2d)
+    _lib.check(_lib.load().mn_layernorm(_ptr(x2d), _ptr(y), _ptr(gamma), _ptr(beta), rows, dim, eps, _stream()), "mn_layernorm")
+    LAUNCHES += 1
+    return y
+
+
+def token_mix(x, gamma, beta, w, bias, eps=1e-5):
+    """x: [B,T,D] contiguous -> [B,To,D]."""
+    global LAUNCHES
+    b, t, d = x.shape
+    to = w.shape[0]
+    out = torch.empty((b, to, d), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().mn_token_mix(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(w), _ptr(bias), _ptr(out), b, t, to, d, eps,
+                                        _stream()), "mn_token_mix")
+    LAUNCHES += 1
+    return out
+
+
+def attention(qkv, heads=8, dh=64):
+    """qkv: [B,S,3*heads*dh] contiguous -> [B,S,heads*dh]."""
+    global LAUNCHES
+    b, s, _ = qkv.shape
+    out = torch.empty((b, s, heads * dh), dtype=torch.float32, device=qkv.device)
+    _lib.check(_lib.load().mn_attention(_ptr(qkv), _ptr(out), b, s, heads, dh, dh ** -0.5, _stream()), "mn_attention")
+    LAUNCHES += 1
+    return out
+
+
+def nchw_to_nhwc(x, out=None):
+    global LAUNCHES
+    _require_cuda(x, "x")
+    n, c, h, w = x.shape
+    x = x.contiguous()
+    y = out if out is not None else torch.empty((n, h, w, c), dtype=torch.float32, device=x.device)
+    _, _, _, _, y_cs = nhwc_info(y, "out")
+    _lib.check(_lib.load().mn_nchw_to_nhwc(_ptr(x), _ptr(y), n, c, h, w, y_cs, _stream()), "mn_nchw_to_nhwc")
+    LAUNCHES += 1
+    return y
+
+
+def nhwc_to_nchw(x):
+    global LAUNCHES
+    n, h, w, c, x_cs = nhwc_info(x, "x")
+    y = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().mn_nhwc_to_nchw(_ptr(x), x_cs, _ptr(y), n, c, h, w, _stream()), "mn_nhwc_to_nchw")
+    LAUNCHES += 1
+    return y
+
+
+def as_nhwc(x_nchw):
+    """NCHW-shaped tensor -> NHWC view, zero-copy when the input is channels_last."""
+    n, c, h, w = x_nchw.shape
+    v = x_nchw.permute(0, 2, 3, 1)
+    if v.is_contiguous():
+        return v
+    return nchw_to_nhwc(x_nchw)
+
+
+def as_nchw_view(x_nhwc):
+    """NHWC tensor -> NCHW-shaped view (channels_last strides); what the modules return."""
+    return x_nhwc.permute(0, 3, 1, 2)

@@ -1,0 +1,266 @@
+"""Per-operator parity of the CUDA kernels (through the C ABI) against plain fp32 torch CPU ops."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+def _nhwc(x):   # NCHW cpu -> NHWC cuda
+    return x.permute(0, 2, 3, 1).contiguous().to(_dev())
+
+
+def _nchw(y):   # NHWC cuda -> NCHW cpu
+    return y.permute(0, 3, 1, 2).cpu()
+
+
+def _pack(w):
+    cout, cin, kh, kw = w.shape
+    return w.permute(2, 3, 1, 0).reshape(kh * kw * cin, cout).contiguous().to(_dev())
+
+
+def _close(a, b, tol, what=""):
+    err = (a - b).abs().max().item()
+    ref = b.abs().max().item()
+    assert err <= tol * max(1.0, ref), f"{what}: max abs err {err:.3e} (ref max {ref:.3e})"
+
+
+CONV_CASES = [
+    # N, H, W, Cin, Cout, k, stride, pad
+    (2, 16, 24, 64, 128, 3, (1, 1), 1),
+    (1, 32, 64, 3, 64, 3, (1, 1), 1),       # Cin=3 generic-K path
+    (1, 16, 40, 64, 3, 3, (1, 1), 1),       # Cout=3 scalar-B path
+    (2, 16, 32, 32, 32, 3, (2, 1), 1),      # ResNet stride (2,1)
+    (1, 32, 48, 64, 128, 3, (2, 2), 1),     # SR stride 2
+    (3, 8, 8, 128, 256, 1, (1, 1), 0),      # 1x1
+    (2, 8, 64, 32, 48, 8, (8, 8), 0),       # patch-embedding style 8x8/8
+    (5, 4, 4, 512, 512, 3, (1, 1), 1),      # tiny spatial, deep K (auto split-K)
+    (1, 1, 1, 512, 6736, 1, (1, 1), 0),     # linear head, M=1
+    (70, 1, 1, 256, 2, 1, (1, 1), 0),       # Cout=2
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_plain(case):
+    from marconet_b200 import ops
+    n, h, w, cin, cout, k, stride, pad = case
+    x = _rand(n, cin, h, w, seed=1)
+    wt = _rand(cout, cin, k, k, seed=2, scale=1.0 / math.sqrt(cin * k * k))
+    ref = F.conv2d(x, wt, stride=stride, padding=pad)
+    y = ops.conv2d(_nhwc(x), _pack(wt), k, k, stride=stride, pad=(pad, pad))
+    _close(_nchw(y), ref, 2e-5, f"conv {case}")
+
+
+def test_conv_forced_splitk_matches():
+    from marconet_b200 import ops
+    x = _rand(2, 256, 8, 8, seed=3)
+    wt = _rand(128, 256, 3, 3, seed=4, scale=0.02)
+    ref = F.conv2d(x, wt, padding=1)
+    for sk in (1, 3, 8):
+        y = ops.conv2d(_nhwc(x), _pack(wt), 3, 3, pad=(1, 1), split_k=sk)
+        _close(_nchw(y), ref, 2e-5, f"split_k={sk}")
+
+
+@pytest.mark.parametrize("act", ["none", "relu", "lrelu", "tanh", "gelu", "sigmoid"])
+def test_conv_epilogue(act):
+    from marconet_b200 import ops
+    n, h, w, cin, cout = 3, 8, 12, 64, 96
+    x = _rand(n, cin, h, w, seed=5)
+    wt = _rand(cout, cin, 3, 3, seed=6, scale=0.05)
+    bias = _rand(cout, seed=7)
+    osc = _rand(n, cout, seed=8).abs() + 0.5
+    res = _rand(n, cout, h, w, seed=9)
+    y2s = _rand(n, cout, seed=10)
+    conv = F.conv2d(x, wt, padding=1) * osc[:, :, None, None] + bias[None, :, None, None] + res
+    fn = dict(none=lambda t: t, relu=F.relu, lrelu=lambda t: F.leaky_relu(t, 0.2), tanh=torch.tanh, gelu=F.gelu,
+              sigmoid=torch.sigmoid)[act]
+    code = dict(none=ops.ACT_NONE, relu=ops.ACT_RELU, lrelu=ops.ACT_LRELU02, tanh=ops.ACT_TANH, gelu=ops.ACT_GELU,
+                sigmoid=ops.ACT_SIGMOID)[act]
+    ref = fn(conv) * 1.25
+    ref2 = ref * y2s[:, :, None, None]
+    d = _dev()
+    y, y2 = ops.conv2d(_nhwc(x), _pack(wt), 3, 3, pad=(1, 1), bias=bias.to(d), out_scale=osc.to(d), residual=_nhwc(res),
+                       act=code, gain=1.25, out2=True, y2_scale=y2s.to(d))
+    _close(_nchw(y), ref, 2e-5, "y")
+    _close(_nchw(y2), ref2, 2e-5, "y2")
+
+
+def test_conv_channel_slices_and_strided_scales():
+    """Reads a channel slice of a concat buffer, writes into a slice, scale rows with a stride."""
+    from marconet_b200 import ops
+    d = _dev()
+    n, h, w = 2, 8, 8
+    buf_in = _rand(n, h, w, 96, seed=11).to(d)
+    xin = buf_in[..., 32:96]                       # Cin=64 view, cs=96
+    wt = _rand(48, 64, 3, 3, seed=12, scale=0.05)
+    big = _rand(n, 200, seed=13).to(d)
+    osc = big[:, 100:148]                          # [n,48] view with row stride 200
+    out_buf = torch.zeros(n, h, w, 80, device=d)
+    ops.conv2d(xin, _pack(wt), 3, 3, pad=(1, 1), out_scale=osc, out=out_buf[..., 16:64])
+    ref = F.conv2d(xin.permute(0, 3, 1, 2).cpu(), wt, padding=1) * osc.cpu()[:, :, None, None]
+    _close(_nchw(out_buf[..., 16:64]), ref, 2e-5)
+    assert out_buf[..., :16].abs().max().item() == 0 and out_buf[..., 64:].abs().max().item() == 0
+
+
+def test_conv_ragged_valid_w():
+    from marconet_b200 import ops
+    d = _dev()
+    n, h, w, c = 3, 8, 16, 32
+    valid = [16, 9, 1]
+    x = _rand(n, c, h, w, seed=14)
+    for i, v in enumerate(valid):
+        x[i, :, :, v:] = 0
+    wt = _rand(64, c, 3, 3, seed=15, scale=0.1)
+    bias = _rand(64, seed=16)
+    y = ops.conv2d(_nhwc(x), _pack(wt), 3, 3, pad=(1, 1), bias=bias.to(d), valid_w=torch.tensor(valid, dtype=torch.int32, device=d))
+    y = _nchw(y)
+    for i, v in enumerate(valid):
+        ref = F.conv2d(x[i:i + 1, :, :, :v], wt, bias, padding=1)      # the window as an isolated image
+        _close(y[i:i + 1, :, :, :v], ref, 2e-5, f"window {i}")
+        assert y[i, :, :, v:].abs().max().item() == 0 if v < w else True
+
+
+def test_broadcast_residual():
+    from marconet_b200 import ops
+    d = _dev()
+    x = _rand(3, 32, 1, 8, seed=17)
+    wt = _rand(64, 32, 1, 1, seed=18)
+    pe = _rand(1, 64, 1, 8, seed=19)
+    y = ops.conv2d(_nhwc(x), _pack(wt), 1, 1, residual=_nhwc(pe), res_broadcast=True)
+    _close(_nchw(y), F.conv2d(x, wt) + pe, 2e-5)
+
+
+def test_pixelnorm_selecttext_demod():
+    from marconet_b200 import ops
+    d = _dev()
+    x = _rand(5, 512, seed=20)
+    _close(ops.pixelnorm(x.to(d)).cpu(), x * torch.rsqrt(torch.mean(x ** 2, dim=1, keepdim=True) + 1e-8), 1e-6)
+    emb = _rand(50, 64, seed=21)
+    labels = torch.tensor([[3, 49], [0, 7], [11, 11]])
+    s = _rand(3, 64, seed=22)
+    out = ops.select_text(emb.to(d), labels.reshape(-1).to(d), s.to(d), 3, 2)      # [3,4,8,64]
+    ref = (emb[labels] * s[:, None, :])                                             # [3,2,64]
+    ref = ref[:, None, :, None, :].expand(3, 4, 2, 4, 64).reshape(3, 4, 8, 64)
+    _close(out.cpu(), ref, 1e-6)
+    wsq = _rand(64, 40, seed=23).abs()
+    dm = ops.demod(s.to(d), wsq.to(d))
+    _close(dm.cpu(), torch.rsqrt((s ** 2) @ wsq + 1e-8), 1e-5)
+
+
+@pytest.mark.parametrize("up", [False, True])
+def test_resample_modulate(up):
+    from marconet_b200 import ops
+    d = _dev()
+    x = _rand(2, 32, 5, 7, seed=24)
+    s = _rand(2, 32, seed=25)
+    ref = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False) if up else x
+    _close(_nchw(ops.resample_modulate(_nhwc(x), None, up=up)), ref, 1e-6)
+    _close(_nchw(ops.resample_modulate(_nhwc(x), s.to(d), up=up)), ref * s[:, :, None, None], 1e-6)
+
+
+@pytest.mark.parametrize("c", [128, 256, 512])
+def test_torgb(c):
+    from marconet_b200 import ops
+    d = _dev()
+    n, h, w = 2, 8, 12
+    x = _rand(n, c, h, w, seed=26)
+    s = _rand(n, c, seed=27)
+    wt = _rand(3, c, seed=28, scale=1 / math.sqrt(c))
+    bias = _rand(3, seed=29)
+    skip = torch.tanh(_rand(n, 3, h // 2, w // 2, seed=30))
+    base = torch.einsum("nchw,nc,oc->nohw", x, s, wt) + bias[None, :, None, None]
+    out = ops.torgb(_nhwc(x), s.to(d), wt.to(d), bias.to(d), None)
+    _close(_nchw(out), torch.tanh(base), 2e-5)
+    out = ops.torgb(_nhwc(x), s.to(d), wt.to(d), bias.to(d), _nhwc(skip))
+    _close(_nchw(out), torch.tanh(base + F.interpolate(skip, scale_factor=2, mode="bilinear", align_corners=False)), 2e-5)
+
+
+def test_groupnorm_swish_full_and_ragged():
+    from marconet_b200 import ops
+    d = _dev()
+    n, c, h, w = 3, 64, 8, 16
+    x = _rand(n, c, h, w, seed=31) * 3 + 1
+    g, b = _rand(c, seed=32), _rand(c, seed=33)
+    ref = F.group_norm(x, c // 32, g, b, eps=1e-6)
+    ref = ref * torch.sigmoid(ref)
+    _close(_nchw(ops.groupnorm_swish(_nhwc(x), g.to(d), b.to(d))), ref, 2e-5)
+    valid = [16, 5, 11]
+    y = _nchw(ops.groupnorm_swish(_nhwc(x), g.to(d), b.to(d), valid_w=torch.tensor(valid, dtype=torch.int32, device=d)))
+    for i, v in enumerate(valid):
+        r = F.group_norm(x[i:i + 1, :, :, :v], c // 32, g, b, eps=1e-6)
+        _close(y[i:i + 1, :, :, :v], r * torch.sigmoid(r), 2e-5, f"ragged {i}")
+        if v < w:
+            assert y[i, :, :, v:].abs().max().item() == 0
+
+
+def test_adain_concat_and_scatter():
+    from marconet_b200 import ops
+    from oracle import restate
+    d = _dev()
+    b, h, w, c, wp = 2, 8, 64, 32, 16
+    feat = _rand(b, c, h, w, seed=34)
+    prior = _rand(3, c, h, wp, seed=35) * 2 + 0.5
+    wins = [(0, 0, 10, 3), (0, 8, 24, 0), (1, 50, 64, 1)]       # (line, x1, x2, y1); 0 and 1 overlap on 8..10
+    win_dev = torch.tensor(wins, dtype=torch.int32, device=d)
+    out = ops.adain_concat(_nhwc(prior), _nhwc(feat), win_dev, 3, wp).cpu()      # [3,h,wp,2c]
+    for i, (ln, x1, x2, y1) in enumerate(wins):
+        wv = x2 - x1
+        cp, cl = prior[i:i + 1, :, :, y1:y1 + wv], feat[ln:ln + 1, :, :, x1:x2]
+        ref = torch.cat((restate._adain(cp, cl), cl), dim=1)
+        _close(out[i:i + 1, :, :wv].permute(0, 3, 1, 2), ref, 2e-5, f"adain {i}")
+        assert out[i, :, wv:].abs().max().item() == 0
+    scale, shift = _rand(3, h, wp, c, seed=36), _rand(3, h, wp, c, seed=37)
+    owner = torch.full((b, w), -1, dtype=torch.int32)
+    for i, (ln, x1, x2, _) in enumerate(wins):
+        owner[ln, x1:x2] = i
+    y = ops.window_scatter(_nhwc(feat), scale.to(d), shift.to(d), owner.to(d), win_dev, wp)
+    ref = feat.clone()
+    for i, (ln, x1, x2, _) in enumerate(wins):
+        sc = scale[i, :, :x2 - x1].permute(2, 0, 1)
+        sh = shift[i, :, :x2 - x1].permute(2, 0, 1)
+        ref[ln, :, :, x1:x2] = feat[ln, :, :, x1:x2] + (feat[ln, :, :, x1:x2] * sc + sh)
+    _close(_nchw(y), ref, 1e-6)
+
+
+def test_layernorm_tokenmix_attention():
+    from marconet_b200 import ops
+    d = _dev()
+    x = _rand(70, 512, seed=38) * 2 + 0.3
+    g, b = _rand(512, seed=39), _rand(512, seed=40)
+    _close(ops.layernorm(x.to(d), g.to(d), b.to(d)).cpu(), F.layer_norm(x, (512,), g, b), 2e-5)
+    xt = _rand(2, 64, 512, seed=41)
+    g, b = _rand(64, seed=42), _rand(64, seed=43)
+    w, bias = _rand(16, 64, seed=44, scale=0.125), _rand(16, seed=45)
+    ref = F.linear(F.layer_norm(xt.permute(0, 2, 1), (64,), g, b), w, bias).permute(0, 2, 1)
+    _close(ops.token_mix(xt.to(d), g.to(d), b.to(d), w.to(d), bias.to(d)).cpu(), ref, 2e-5)
+    for s in (64, 16):
+        qkv = _rand(2, s, 1536, seed=46 + s)
+        q, k, v = [t.reshape(2, s, 8, 64).permute(0, 2, 1, 3) for t in qkv.chunk(3, dim=-1)]
+        ref = (torch.softmax(q @ k.transpose(-1, -2) * 0.125, dim=-1) @ v).permute(0, 2, 1, 3).reshape(2, s, 512)
+        _close(ops.attention(qkv.to(d)).cpu(), ref, 2e-5, f"attention S={s}")
+
+
+def test_layout_roundtrip():
+    from marconet_b200 import ops
+    d = _dev()
+    x = _rand(2, 37, 5, 9, seed=50)
+    y = ops.nchw_to_nhwc(x.to(d))
+    assert torch.equal(y.cpu(), x.permute(0, 2, 3, 1).contiguous())
+    assert torch.equal(ops.nhwc_to_nchw(y).cpu(), x)
+
+
+def test_cpu_tensor_is_rejected_loudly():
+    from marconet_b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.pixelnorm(torch.randn(2, 8))

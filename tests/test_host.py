@@ -1,0 +1,91 @@
+"""CPU tests of the host side: C-ABI library loads and exports every declared symbol, the module mirror
+strict-loads reference-format checkpoints, window arithmetic, loud failure without CUDA."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from marconet_b200 import _lib, build
+    build.build()
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "marconet_b200.h")).read()
+    declared = set(re.findall(r"\b(mn_[a-z0-9_]+)\s*\(", header))
+    declared -= {"mn_status", "mn_act", "mn_precision"}
+    assert declared, "no declarations parsed"
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(raw, name), f"{name} declared in include/marconet_b200.h but not exported"
+        assert name in _lib.SYMBOLS, f"{name} has no ctypes binding"
+    assert lib.mn_version() >= 100
+
+
+def test_conv_params_struct_matches_header_field_order():
+    from marconet_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "marconet_b200.h")).read()
+    body = header.split("typedef struct {", 1)[1].split("} mn_conv_params;")[0]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        parts = [p.strip() for p in decl.split(",")]
+        names.append(re.findall(r"[A-Za-z_0-9]+$", parts[0])[0])
+        names += [re.findall(r"[A-Za-z_0-9]+$", p)[0] for p in parts[1:]]
+    assert names == [f[0] for f in _lib.ConvParams._fields_]
+
+
+def test_strict_load_and_param_counts(checkpoints):
+    from marconet_b200.models import networks
+    want = {"tspgan": 27970194, "encoder": 43062275, "sr": 16865923}       # banner of test_sr.py:59-61
+    for key, cls in (("tspgan", networks.TSPGAN), ("encoder", networks.TextContextEncoderV2), ("sr", networks.TSPSRNet)):
+        m = cls()
+        m.load_state_dict(checkpoints[key], strict=True)
+        assert list(m.state_dict().keys()) == list(checkpoints[key].keys())
+        assert sum(p.numel() for p in m.parameters()) == want[key]
+        for k, v in m.state_dict().items():
+            assert v.shape == checkpoints[key][k].shape
+
+
+def test_helper_classes_importable_under_reference_names():
+    import importlib
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "dropin"))
+    try:
+        for name in [m for m in sys.modules if m == "models" or m.startswith("models.")]:
+            del sys.modules[name]
+        nets = importlib.import_module("models.networks")
+        importlib.import_module("models.ocr")
+        for cls in ("TSPGAN", "TextGenerator", "TSPSRNet", "TextContextEncoderV2", "StyledConv", "ModulatedConv2d", "ToRGB",
+                    "EqualLinear", "SelectText", "PixelNorm", "ResTextBlockV2"):
+            assert hasattr(nets, cls), cls
+    finally:
+        sys.path.remove(os.path.join(ROOT, "dropin"))
+        for name in [m for m in sys.modules if m == "models" or m.startswith("models.")]:
+            del sys.modules[name]
+
+
+def test_cpu_inputs_fail_loudly(checkpoints):
+    from marconet_b200.models import networks
+    m = networks.TSPGAN()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.randn(1, 512), torch.zeros(1, 1, dtype=torch.long), None)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        networks.TextContextEncoderV2()(torch.randn(1, 3, 32, 512))
+
+
+def test_char_windows_ownership_last_writer_wins():
+    from marconet_b200.models.networks import char_windows
+    locs = torch.tensor([[100.2 / 512, 0.03, 110.9 / 512, 0.03, 3.0 / 512, 0.03, 509.0 / 512, 0.03]])
+    wins, valid, owner = char_windows(locs, [4], 512, 16)
+    assert wins == [(0, 84, 116, 0), (0, 94, 126, 0), (0, 0, 19, 7), (0, 493, 512, 7)]
+    assert valid == [32, 32, 19, 19]
+    assert owner[0][90] == 0 and owner[0][100] == 1 and owner[0][120] == 1 and owner[0][5] == 2 and owner[0][200] == -1
+    with pytest.raises(RuntimeError):
+        char_windows(torch.tensor([[-0.2, 0.0]]), [1], 512, 16)
