@@ -219,7 +219,8 @@ def test_adain_concat_and_scatter():
         cp, cl = prior[i:i + 1, :, :, y1:y1 + wv], feat[ln:ln + 1, :, :, x1:x2]
         ref = torch.cat((restate._adain(cp, cl), cl), dim=1)
         _close(out[i:i + 1, :, :wv].permute(0, 3, 1, 2), ref, 2e-5, f"adain {i}")
-        assert out[i, :, wv:].abs().max().item() == 0
+        if wv < wp:
+            assert out[i, :, wv:].abs().max().item() == 0
     scale, shift = _rand(3, h, wp, c, seed=36), _rand(3, h, wp, c, seed=37)
     owner = torch.full((b, w), -1, dtype=torch.int32)
     for i, (ln, x1, x2, _) in enumerate(wins):
