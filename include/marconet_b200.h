@@ -88,11 +88,22 @@ typedef struct {
     float* workspace; int64_t workspace_bytes; /* split-K partial sums; may be NULL (no split)  */
     int split_k;                               /* 0 = choose automatically, 1 = never split     */
     int precision;                             /* mn_precision                                  */
+    /* tensor-core precisions only: weights pre-split by mn_conv_pack_weights_tc()                */
+    const void* w_tc_hi; const void* w_tc_lo;  /* 16-bit [KH*KW][Cout][Cin] (K-major)            */
+    const float* w_tc_scale;                   /* the 2-float scale record written by the packer */
 } mn_conv_params;
 
 int mn_conv2d_nhwc(const mn_conv_params* p, void* stream);
 /* Bytes of workspace mn_conv2d_nhwc wants for this problem (0 if it will not split). */
 int64_t mn_conv2d_workspace_bytes(const mn_conv_params* p);
+/* 1 if the tcgen05 path can run this geometry (stride 1, 3x3/pad1 or 1x1, Cin%64==0, Cout%64==0,
+ * pixel tiles of 128 that tile [N,H,W] exactly); 0 otherwise (mn_last_error() says why). */
+int mn_conv2d_tc_supported(const mn_conv_params* p);
+/* Split fp32 weights w:[taps*Cin][Cout] (the layout mn_conv2d_nhwc takes) into hi/lo 16-bit planes
+ * [taps][Cout][Cin], pre-scaled by a power of two so the lo plane stays in the fp16 normal range.
+ * hi, lo: taps*Cin*Cout 16-bit elements each; scale2: 2 floats {abs-max, 2^-S}. */
+int mn_conv_pack_weights_tc(const float* w, int taps, int Cin, int Cout, int precision, void* hi, void* lo,
+                            float* scale2, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Generator (TSPGAN) operators

@@ -31,6 +31,7 @@ class ConvParams(Structure):
         ("workspace", c_void_p), ("workspace_bytes", c_int64),
         ("split_k", c_int),
         ("precision", c_int),
+        ("w_tc_hi", c_void_p), ("w_tc_lo", c_void_p), ("w_tc_scale", c_void_p),
     ]
 
 
@@ -45,6 +46,8 @@ SYMBOLS = {
     "mn_device_is_sm100": (c_int, []),
     "mn_conv2d_nhwc": (c_int, [POINTER(ConvParams), c_void_p]),
     "mn_conv2d_workspace_bytes": (c_int64, [POINTER(ConvParams)]),
+    "mn_conv2d_tc_supported": (c_int, [POINTER(ConvParams)]),
+    "mn_conv_pack_weights_tc": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mn_pixelnorm": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "mn_select_text": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
     "mn_demod": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),

@@ -47,8 +47,21 @@ extern "C" int mn_conv2d_nhwc(const mn_conv_params* p, void* stream) {
         case MN_PREC_FP32_SIMT:
             g.splits = mn_conv_simt_plan_splits(g, p->workspace ? p->workspace_bytes : 0, p->split_k);
             return mn_conv_simt_launch(g, nullptr, st);
+        case MN_PREC_F16X3_TC:
+        case MN_PREC_BF16X3_TC:
+        case MN_PREC_F16X1_TC:
+            return mn_conv_tc_launch(g, p->w_tc_hi, p->w_tc_lo, p->w_tc_scale, p->precision, st);
         default:
-            mn_set_error("mn_conv2d_nhwc: precision mode %d not available in this build", p->precision);
+            mn_set_error("mn_conv2d_nhwc: unknown precision mode %d", p->precision);
             return MN_ERR_UNSUPPORTED;
     }
+}
+
+extern "C" int mn_conv2d_tc_supported(const mn_conv_params* p) {
+    ConvGeom g;
+    if (make_geom(p, g) != MN_OK) return 0;
+    const char* why = "";
+    const int ok = mn_conv_tc_supported(g, &why);
+    if (!ok) mn_set_error("tensor-core path unsupported: %s", why);
+    return ok;
 }

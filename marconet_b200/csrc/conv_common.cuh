@@ -58,3 +58,7 @@ __device__ __forceinline__ void conv_epilogue4(const ConvGeom& g, int m, int o, 
 
 int mn_conv_simt_plan_splits(const ConvGeom& g, int64_t ws_bytes, int requested);
 int mn_conv_simt_launch(ConvGeom g, const float* unused, cudaStream_t st);
+
+// tcgen05 path (conv_tc.cu)
+int mn_conv_tc_supported(const ConvGeom& g, const char** why);
+int mn_conv_tc_launch(const ConvGeom& g, const void* w_hi, const void* w_lo, const float* w_scale, int prec, cudaStream_t st);

@@ -65,9 +65,9 @@ class _PackedModule(nn.Module):
 
 
 def _pack_conv_weight(w):
-    """[Cout, Cin, KH, KW] -> K-major [KH*KW*Cin, Cout] fp32 contiguous."""
+    """[Cout, Cin, KH, KW] -> ops.ConvWeight (K-major [KH*KW*Cin, Cout] fp32 + lazily split 16-bit planes)."""
     cout, cin, kh, kw = w.shape
-    return w.permute(2, 3, 1, 0).reshape(kh * kw * cin, cout).contiguous()
+    return ops.ConvWeight(w.permute(2, 3, 1, 0).reshape(kh * kw * cin, cout).contiguous(), kh * kw)
 
 
 # =========================================================================================

@@ -17,7 +17,7 @@ _STAGES = ((32, 3, (2, 1)), (64, 4, (1, 1)), (128, 6, (2, 1)), (256, 6, (1, 1)),
 
 def _pack(w):
     cout, cin, kh, kw = w.shape
-    return w.detach().permute(2, 3, 1, 0).reshape(kh * kw * cin, cout).contiguous()
+    return ops.ConvWeight(w.detach().permute(2, 3, 1, 0).reshape(kh * kw * cin, cout).contiguous(), kh * kw)
 
 
 def conv1x1(in_planes, out_planes, stride=1):

@@ -17,7 +17,7 @@ from ..ops import ACT_GELU, ACT_SIGMOID
 
 def _lin(m):
     """nn.Linear -> ([in,out] packed weight, bias or None)."""
-    return m.weight.detach().t().contiguous(), (None if m.bias is None else m.bias.detach().contiguous())
+    return ops.ConvWeight(m.weight.detach().t().contiguous(), 1), (None if m.bias is None else m.bias.detach().contiguous())
 
 
 def _ln(m):
@@ -117,7 +117,7 @@ class TextViT(nn.Module):
         if s != 64:
             raise RuntimeError("TextViT is built for 32x512 LR lines (64 tokens)")
         pw, pb = pk["patch"]
-        x = ops.conv2d(feat, pw, 8, 8, stride=(8, 8), bias=pb, residual=pk["pe"].view(1, 1, s, -1), res_broadcast=True)
+        x = ops.conv2d(feat, pw.w, 8, 8, stride=(8, 8), bias=pb, residual=pk["pe"].view(1, 1, s, -1), res_broadcast=True)
         x = x.view(b * s, self.dim)
         for blk in pk["layers"]:
             x = _block_run(blk, x, b, s)

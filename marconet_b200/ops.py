@@ -66,6 +66,44 @@ def workspace(device):
     return ws
 
 
+class ConvWeight:
+    """A conv/linear weight in kernel layout: fp32 K-major [KH*KW*Cin, Cout] plus (lazily) the hi/lo 16-bit
+    planes [taps][Cout][Cin] the tcgen05 path consumes (mn_conv_pack_weights_tc)."""
+
+    __slots__ = ("w", "taps", "cin", "cout", "_tc")
+
+    def __init__(self, w, taps):
+        self.w = w
+        self.taps = taps
+        self.cin = w.shape[0] // taps
+        self.cout = w.shape[1]
+        self._tc = {}
+
+    @property
+    def shape(self):
+        return self.w.shape
+
+    def tc_capable(self):
+        return self.cin % 64 == 0 and self.cout % 64 == 0
+
+    def tc(self, precision):
+        key = PREC_BF16X3_TC if precision == PREC_BF16X3_TC else PREC_F16X3_TC
+        got = self._tc.get(key)
+        if got is None:
+            n = self.taps * self.cin * self.cout
+            hi = torch.empty(n, dtype=torch.int16, device=self.w.device)
+            lo = torch.empty(n, dtype=torch.int16, device=self.w.device)
+            sc = torch.empty(2, dtype=torch.float32, device=self.w.device)
+            _lib.check(_lib.load().mn_conv_pack_weights_tc(_ptr(self.w), self.taps, self.cin, self.cout, key, _ptr(hi), _ptr(lo),
+                                                           _ptr(sc), _stream()), "mn_conv_pack_weights_tc")
+            got = (hi, lo, sc)
+            self._tc[key] = got
+        return got
+
+
+TC_MIN_FLOP = 2.0e8    # below this a launch is latency-bound either way; stay on the exact fp32 path
+
+
 def conv2d(x, w, kh, kw, stride=(1, 1), pad=(0, 0), bias=None, out_scale=None, residual=None,
            res_broadcast=False, act=ACT_NONE, gain=1.0, out=None, out2=None, y2_scale=None,
            valid_w=None, precision=None, want_y=True, split_k=0):
@@ -73,6 +111,9 @@ def conv2d(x, w, kh, kw, stride=(1, 1), pad=(0, 0), bias=None, out_scale=None, r
     global LAUNCHES
     lib = _lib.load()
     n, h, wd, cin, x_cs = nhwc_info(x, "x")
+    cw = w if isinstance(w, ConvWeight) else None
+    if cw is not None:
+        w = cw.w
     cout = w.shape[1]
     if w.shape[0] != kh * kw * cin:
         raise RuntimeError(f"conv2d: packed weight has {w.shape[0]} rows, expected {kh * kw * cin}")
@@ -108,7 +149,20 @@ def conv2d(x, w, kh, kw, stride=(1, 1), pad=(0, 0), bias=None, out_scale=None, r
     ws = workspace(x.device)
     p.workspace = ws.data_ptr(); p.workspace_bytes = ws.numel() * 4
     p.split_k = split_k
-    p.precision = _DEFAULT_PRECISION if precision is None else precision
+    prec = _DEFAULT_PRECISION if precision is None else precision
+    if prec != PREC_FP32_SIMT:
+        use_tc = (cw is not None and cw.tc_capable() and stride == (1, 1)
+                  and (precision is not None or 2.0 * n * oh * ow * cout * kh * kw * cin >= TC_MIN_FLOP)
+                  and lib.mn_conv2d_tc_supported(ctypes.byref(p)) == 1)
+        if use_tc:
+            hi, lo, sc = cw.tc(prec)
+            p.w_tc_hi = hi.data_ptr(); p.w_tc_lo = lo.data_ptr(); p.w_tc_scale = sc.data_ptr()
+        elif precision is not None:
+            raise RuntimeError("conv2d: tensor-core precision requested explicitly but this layer/shape is not supported: "
+                               + lib.mn_last_error().decode(errors="replace"))
+        else:
+            prec = PREC_FP32_SIMT
+    p.precision = prec
     _lib.check(lib.mn_conv2d_nhwc(ctypes.byref(p), _stream()), "mn_conv2d_nhwc")
     LAUNCHES += 1
     if y2 is not None:
