@@ -15,7 +15,8 @@ from ._lib import (ACT_GELU, ACT_LRELU02, ACT_NONE, ACT_RELU, ACT_RSQRT_EPS, ACT
 
 _WS = {}
 _WS_BYTES = 96 << 20
-_DEFAULT_PRECISION = PREC_FP32_SIMT
+import os as _os
+_DEFAULT_PRECISION = int(_os.environ.get("MN_PRECISION", PREC_FP32_SIMT))   # 0 fp32 SIMT, 1 fp16x3 TC, 2 bf16x3 TC, 3 fp16x1 TC
 LAUNCHES = 0   # number of C-ABI kernel-launching calls issued (bench.py reports it)
 
 

@@ -46,7 +46,8 @@ TC_CASES = [
     (1, 32, 32, 512, 512, 3),     # deep K: 72 k-blocks, many pipeline wraps
     (70, 1, 1, 512, 1024, 1),     # a linear layer: [M,1,1,K]
 ]
-TOL = {"f16x3": 1e-5, "bf16x3": 2e-3, "f16x1": 4e-3}
+# tensor-core fp32 accumulation truncates (round-toward-zero): the error grows ~linearly with K/16 accumulation steps
+TOL = {"f16x3": 4e-5, "bf16x3": 2e-4, "f16x1": 4e-3}
 
 
 @pytest.mark.parametrize("mode", ["f16x3", "bf16x3", "f16x1"])
