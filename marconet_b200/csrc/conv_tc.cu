@@ -148,8 +148,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmBlo, const ConvGeom g, const TcGeom t) {
     constexpr int B_BYTES = NT * 128;
     constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;
-    constexpr int A_COL0 = NT;                   // TMEM: D in [0,NT), A(stage s) hi at NT+64s, lo at NT+64s+32
-    static_assert(NT + STAGES * 64 <= TMEM_COLS, "TMEM budget");
+    // TMEM columns: D (hi*hi products) in [0,NT), Dc (hi*lo + lo*hi correction products) in [NT,2NT),
+    // A(stage s) hi at 2NT+64s, lo at 2NT+64s+32.  The tensor core TRUNCATES when it adds into the fp32
+    // accumulator, so the error of a long K loop is a bias ~ (#accumulations) * ulp(|D|)/2.  Keeping the two
+    // small cross terms in their own accumulator (2^-11 the magnitude) leaves only K/16 truncations at full
+    // magnitude instead of 3K/16 and the final D + Dc is one round-to-nearest fp32 add in the epilogue.
+    constexpr int A_COL0 = 2 * NT;
+    static_assert(2 * NT + STAGES * 64 <= TMEM_COLS, "TMEM budget");
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -227,8 +232,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     tc_mma_ts(tmem_base, a_hi + j * 8, dh, idesc, (kb | j) != 0);
                     if (three) {
                         const uint64_t dl = make_b_desc(b_lo + j * 32);
-                        tc_mma_ts(tmem_base, a_hi + j * 8, dl, idesc, 1);
-                        tc_mma_ts(tmem_base, a_hi + 32 + j * 8, dh, idesc, 1);
+                        tc_mma_ts(tmem_base + NT, a_hi + j * 8, dl, idesc, (kb | j) != 0);
+                        tc_mma_ts(tmem_base + NT, a_hi + 32 + j * 8, dh, idesc, 1);
                     }
                 }
                 tc_commit(bar_empty(s));
@@ -289,7 +294,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int chunk = 0; chunk < NT / 16; ++chunk) {
             uint32_t acc[16];
             tc_ld16(lane_addr + chunk * 16, acc);
-            tc_wait_ld();
+            if (t.prec != MN_PREC_F16X1_TC) {
+                uint32_t cor[16];
+                tc_ld16(lane_addr + NT + chunk * 16, cor);
+                tc_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) acc[i] = __float_as_uint(__uint_as_float(acc[i]) + __uint_as_float(cor[i]));
+            } else {
+                tc_wait_ld();
+            }
             if (row_ok) {
 #pragma unroll
                 for (int k4 = 0; k4 < 4; ++k4) {
@@ -393,8 +406,7 @@ TcPlan plan_tc(const ConvGeom& g) {
     p.t.TW = TW; p.t.TH = TH; p.t.TN = TN;
     p.t.tiles_w = g.W / TW; p.t.tiles_h = g.H / TH; p.t.tiles_n = (g.N + TN - 1) / TN;
     p.t.cblocks = g.Cin / KB; p.t.taps = g.KH * g.KW;
-    if (g.Cout % 256 == 0) { p.NT = 256; p.STAGES = 2; }
-    else if (g.Cout % 128 == 0) { p.NT = 128; p.STAGES = 3; }
+    if (g.Cout % 128 == 0) { p.NT = 128; p.STAGES = 3; }
     else { p.NT = 64; p.STAGES = 4; }
     p.ok = true;
     return p;
@@ -453,7 +465,6 @@ int mn_conv_tc_launch(const ConvGeom& g, const void* w_hi, const void* w_lo, con
     TcGeom t = p.t;
     t.wscale = w_scale + 1;
     t.prec = prec;
-    if (p.NT == 256) return launch_tc<256, 2>(ma, mbh, mbl, g, t, st);
     if (p.NT == 128) return launch_tc<128, 3>(ma, mbh, mbl, g, t, st);
     return launch_tc<64, 4>(ma, mbh, mbl, g, t, st);
 }
