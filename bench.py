@@ -230,6 +230,13 @@ def run_ours(args):
     with torch.no_grad():
         for _ in range(max(args.warmup, 3)):
             step(lq_dev, locs_dev)
+        if args.profile:   # exactly one step between cudaProfilerStart/Stop (ncu --profile-from-start off)
+            torch.cuda.synchronize()
+            torch.cuda.profiler.start()
+            step(lq_dev, locs_dev)
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
+            return
         sampler = ClockSampler(local)
         sampler.start()
         l0 = ops.LAUNCHES
@@ -328,6 +335,7 @@ def main():
     ap.add_argument("--chars", type=int, default=16)
     ap.add_argument("--precision", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="run one step inside cudaProfilerStart/Stop and exit (for ncu)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -13,8 +13,14 @@ import torch
 pytestmark = pytest.mark.gpu
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-TOL = 1e-3          # north_star budget
-TOL_FP32 = 2e-4     # what we hold the fp32 path to
+TOL = 1e-3          # north_star budget (golden-fixture tests assert this)
+
+
+def _tol_internal():
+    """Tighter bound the module-vs-oracle tests hold each path to: 2e-4 for the fp32 CUDA-core path, 5e-4 for the
+    tcgen05 operand-split path (its fp32 TMEM accumulation truncates; see conv_tc.cu)."""
+    from marconet_b200 import ops
+    return 2e-4 if ops.default_precision() == ops.PREC_FP32_SIMT else 5e-4
 
 
 def _maxerr(a, b):
@@ -32,7 +38,7 @@ def test_tspgan_matches_oracle(gpu_models, checkpoints):
     assert img.shape == oi.shape and f64.shape == o64.shape and f32_.shape == o32.shape
     errs = (_maxerr(img, oi), _maxerr(f64, o64), _maxerr(f32_, o32))
     print("tspgan max-abs err (image, fea64, fea32):", errs)
-    assert max(errs) <= TOL_FP32
+    assert max(errs) <= _tol_internal()
 
 
 def test_tspgan_two_labels_per_row_and_errors(gpu_models, checkpoints):
@@ -43,7 +49,7 @@ def test_tspgan_two_labels_per_row_and_errors(gpu_models, checkpoints):
     img, f64, f32_ = gpu_models["tspgan"](styles.to(dev), labels.to(dev), None)
     oi, o64, o32 = restate.tspgan_forward(checkpoints["tspgan"], styles, labels)
     assert tuple(img.shape) == (2, 3, 128, 256)
-    assert max(_maxerr(img, oi), _maxerr(f64, o64), _maxerr(f32_, o32)) <= TOL_FP32
+    assert max(_maxerr(img, oi), _maxerr(f64, o64), _maxerr(f32_, o32)) <= _tol_internal()
     with pytest.raises(IndexError):           # unknown char -> alphabet.find == -1 (test_sr.py:24-29)
         gpu_models["tspgan"](styles.to(dev), torch.tensor([[-1, 3], [1, 2]]), None)
     with pytest.raises(IndexError):
@@ -60,7 +66,7 @@ def test_encoder_matches_oracle_and_argmax_exact(gpu_models, checkpoints):
     ol, olo, ow = restate.encoder_forward(checkpoints["encoder"], lq)
     errs = (_maxerr(logits, ol), _maxerr(locs, olo), _maxerr(w, ow))
     print("encoder max-abs err (logits, locs, w):", errs)
-    assert max(errs) <= TOL_FP32
+    assert max(errs) <= _tol_internal()
     assert torch.equal(logits.argmax(-1).cpu(), ol.argmax(-1)), "char-index integers must be bit-exact"
     for b in range(2):
         assert restate.clear_labels(logits[b].cpu()) == restate.clear_labels(ol[b])
@@ -80,7 +86,7 @@ def test_sr_ragged_matches_oracle(gpu_models, checkpoints):
     assert tuple(sr.shape) == (2, 3, 128, 2048)
     err = _maxerr(sr, ref)
     print("sr (ragged) max-abs err:", err)
-    assert err <= TOL_FP32
+    assert err <= _tol_internal()
 
 
 def test_window_integers_bit_exact():
