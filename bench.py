@@ -333,7 +333,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--lines", type=int, default=1, help="LR lines per GPU per step")
     ap.add_argument("--chars", type=int, default=16)
-    ap.add_argument("--precision", type=int, default=None)
+    ap.add_argument("--precision", type=int, default=None, help="0 fp32 CUDA-core, 1 fp16x3 tcgen05 (default), 2 bf16x3, 3 fp16x1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="run one step inside cudaProfilerStart/Stop and exit (for ncu)")
     args = ap.parse_args()

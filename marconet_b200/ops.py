@@ -16,7 +16,8 @@ from ._lib import (ACT_GELU, ACT_LRELU02, ACT_NONE, ACT_RELU, ACT_RSQRT_EPS, ACT
 _WS = {}
 _WS_BYTES = 96 << 20
 import os as _os
-_DEFAULT_PRECISION = int(_os.environ.get("MN_PRECISION", PREC_FP32_SIMT))   # 0 fp32 SIMT, 1 fp16x3 TC, 2 bf16x3 TC, 3 fp16x1 TC
+# 0 fp32 CUDA-core, 1 fp16x3 tcgen05 (default: parity-grade tensor-core path), 2 bf16x3 tcgen05, 3 fp16x1 tcgen05 (not parity grade)
+_DEFAULT_PRECISION = int(_os.environ.get("MN_PRECISION", PREC_F16X3_TC))
 LAUNCHES = 0   # number of C-ABI kernel-launching calls issued (bench.py reports it)
 
 

@@ -12,6 +12,17 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True, params=["fp16x3_tcgen05", "fp32_simt"])
+def precision_mode(request):
+    """Every module-level parity test runs on both conv paths: the default tcgen05 operand-split path and the
+    exact fp32 CUDA-core path."""
+    from marconet_b200 import ops
+    old = ops.default_precision()
+    ops.set_default_precision(ops.PREC_F16X3_TC if request.param == "fp16x3_tcgen05" else ops.PREC_FP32_SIMT)
+    yield request.param
+    ops.set_default_precision(old)
+
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 TOL = 1e-3          # north_star budget (golden-fixture tests assert this)
 
