@@ -1,0 +1,66 @@
+"""Sharding of the hot path over the GPUs of one box (one process per GPU, torch.distributed / NCCL over NVLink).
+
+Two levels of independence exist:
+  * text lines are fully independent (reference test_sr.py:77): shard lines, no collective;
+  * characters are independent inside TSPGAN (reference networks.py:134-164 has no cross-sample op): shard the
+    characters of a batch over ranks and all-gather the two prior tensors the SR decoder needs for its per-character
+    concat (fea64 [n,256,64,64] + fea32 [n,512,32,32] = 6 MiB fp32 per character) -- the only exchange on the path.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n, rank, world):
+    """Contiguous, balanced [begin, end) of n items for `rank` (first n % world ranks get one extra)."""
+    base, extra = divmod(n, world)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def shard_lines(num_lines, rank=None, world=None):
+    rank = dist.get_rank() if rank is None else rank
+    world = dist.get_world_size() if world is None else world
+    return range(*shard_range(num_lines, rank, world))
+
+
+def _all_gather_rows(local, counts, group):
+    """All-gather tensors whose first dimension differs per rank (padded to the largest shard, then trimmed)."""
+    world = len(counts)
+    mx = max(counts)
+    pad = local
+    if local.shape[0] < mx:
+        pad = torch.zeros((mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        pad[:local.shape[0]] = local
+    pad = pad.contiguous()
+    out = torch.empty((world * mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, pad, group=group)
+    if all(c == mx for c in counts):
+        return out
+    return torch.cat([out[r * mx:r * mx + counts[r]] for r in range(world)], dim=0)
+
+
+def generate_priors_sharded(generator, styles, labels, group=None):
+    """Character-sharded TSPGAN: every rank generates its contiguous shard of the characters and the priors are
+    all-gathered so that every rank holds the full (image, fea64, fea32) -- what TSPSRNet consumes.
+
+    `generator(styles, labels, None) -> (image, fea64, fea32)` is the TSPGAN module (or any callable with its contract);
+    tensors are returned in the generator's own memory format (channels_last views stay channels_last)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n = labels.shape[0]
+    if world == 1:
+        return generator(styles, labels, None)
+    counts = [shard_range(n, r, world)[1] - shard_range(n, r, world)[0] for r in range(world)]
+    b, e = shard_range(n, rank, world)
+    if e > b:
+        outs = generator(styles[b:e], labels[b:e], None)
+    else:   # more ranks than characters: contribute an empty shard of the right trailing shape
+        probe = generator(styles[:1], labels[:1], None)
+        outs = tuple(o[:0] for o in probe)
+    gathered = []
+    for o in outs:
+        cl = o.dim() == 4 and o.permute(0, 2, 3, 1).is_contiguous()          # NHWC storage behind an NCHW-shaped view
+        local = o.permute(0, 2, 3, 1) if cl else o.contiguous()
+        full = _all_gather_rows(local, counts, group)
+        gathered.append(full.permute(0, 3, 1, 2) if cl else full)
+    return tuple(gathered)
