@@ -2,6 +2,13 @@
 #include "mn_common.cuh"
 #include "conv_common.cuh"
 
+#include <stdlib.h>
+static bool tc_force_v1() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MN_TC_V1"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+
 static int make_geom(const mn_conv_params* p, ConvGeom& g) {
     MN_REQUIRE(p != nullptr, "mn_conv2d_nhwc: null params");
     MN_REQUIRE(p->x && p->w && (p->y || p->y2), "mn_conv2d_nhwc: null x/w/y");
@@ -50,6 +57,8 @@ extern "C" int mn_conv2d_nhwc(const mn_conv_params* p, void* stream) {
         case MN_PREC_F16X3_TC:
         case MN_PREC_BF16X3_TC:
         case MN_PREC_F16X1_TC:
+            if (!tc_force_v1() && mn_conv_tc2_supported(g, nullptr))
+                return mn_conv_tc2_launch(g, p->w_tc_hi, p->w_tc_lo, p->w_tc_scale, p->precision, st);
             return mn_conv_tc_launch(g, p->w_tc_hi, p->w_tc_lo, p->w_tc_scale, p->precision, st);
         default:
             mn_set_error("mn_conv2d_nhwc: unknown precision mode %d", p->precision);
@@ -61,7 +70,7 @@ extern "C" int mn_conv2d_tc_supported(const mn_conv_params* p) {
     ConvGeom g;
     if (make_geom(p, g) != MN_OK) return 0;
     const char* why = "";
-    const int ok = mn_conv_tc_supported(g, &why);
+    const int ok = (!tc_force_v1() && mn_conv_tc2_supported(g, nullptr)) || mn_conv_tc_supported(g, &why);
     if (!ok) mn_set_error("tensor-core path unsupported: %s", why);
     return ok;
 }

@@ -62,3 +62,6 @@ int mn_conv_simt_launch(ConvGeom g, const float* unused, cudaStream_t st);
 // tcgen05 path (conv_tc.cu)
 int mn_conv_tc_supported(const ConvGeom& g, const char** why);
 int mn_conv_tc_launch(const ConvGeom& g, const void* w_hi, const void* w_lo, const float* w_scale, int prec, cudaStream_t st);
+// tcgen05 path v2: halo tiles + weight multicast + persistent CTAs (conv_tc2.cu)
+int mn_conv_tc2_supported(const ConvGeom& g, const char** why);
+int mn_conv_tc2_launch(const ConvGeom& g, const void* w_hi, const void* w_lo, const float* w_scale, int prec, cudaStream_t st);

@@ -1,0 +1,432 @@
+// conv_tc2.cu -- second-generation tcgen05 operand-split implicit-GEMM convolution (see conv_tc.cu for the numerics:
+// x*w ~= xh*wh + (xh*wl + xl*wh), two fp32 TMEM accumulators, fp32 activations in HBM, A operand split on the fly into TMEM).
+//
+// v1 (conv_tc.cu) re-loads the 128-pixel activation tile once per tap and every CTA streams its own copy of the weights:
+// 64 KB of L2->SMEM traffic per 768 MMA cycles per SM, i.e. L2-bandwidth bound at ~36 % of the split-precision MMA peak.
+// v2 removes that traffic:
+//   * HALO TILE.  Loop order is (64-channel block) outer, (tap) inner.  One TMA box per channel block brings the
+//     (TH+2) x (TW+2) halo of the 128-pixel output tile (zero-filled outside the image = conv padding); the 9 taps are
+//     9 shifted *reads* of that tile by the split warps (row r of tap (ky,kx) is halo row r0 + ky*(TW+2) + kx).
+//     Activation traffic drops from 9 x 32 KB to ~1.4-1.6 x 32 KB per channel block.
+//   * WEIGHT MULTICAST.  CTAs of a cluster (2 consecutive pixel tiles, same output-channel tile) each load 1/CS of
+//     every weight tile and TMA-multicast it to all; the stage is released by tcgen05.commit multicast to every CTA.
+//   * PERSISTENT tiles: one CTA per SM loops over work items; producers run ahead into the next tile while the split
+//     warps drain TMEM (through a shared-memory staging buffer -> fully coalesced global stores).
+// Warp roles: 0 = weight (B) TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = split + epilogue, 6 = halo TMA producer.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include "conv_common.cuh"
+#include "mn_common.cuh"
+#include "tc_ptx.cuh"
+
+namespace {
+using namespace tcptx;
+
+constexpr int KB = 64;
+constexpr int NUM_THREADS2 = 224;
+constexpr int A_STAGES = 3;
+constexpr int MAX_BSTAGES = 4;
+constexpr int STG_COLS = 64;
+constexpr int STG_PITCH = STG_COLS + 4;
+constexpr int STG_BYTES = 128 * STG_PITCH * 4;
+constexpr int TMEM_COLS2 = 512;
+constexpr int SMEM_LIMIT = 232448;          // 227 KB
+
+struct Tc2Geom {
+    int TW, TH, TN, HWd, HHt, halo_rows, box_bytes, halo_stage_bytes;
+    int tiles_w, tiles_h, tiles_n, m_tiles, m_groups, n_tiles;
+    int cblocks, taps, KW, ph, pw;
+    int bstages, cs;
+    const float* wscale;
+    int prec;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(NUM_THREADS2, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
+                const __grid_constant__ CUtensorMap tmBlo, const ConvGeom g, const Tc2Geom t) {
+    constexpr int B_HALF = NT * 128;              // bytes of one (hi or lo) weight tile
+    constexpr int B_STAGE = 2 * B_HALF;
+    constexpr int A_COL0 = 2 * NT;                // TMEM: D [0,NT), Dc [NT,2NT), A stage s at 2NT+64s (hi) / +32 (lo)
+    static_assert(2 * NT + A_STAGES * 64 <= TMEM_COLS2, "TMEM budget");
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t off_b = 2 * t.halo_stage_bytes;
+    const uint32_t off_stg = off_b + t.bstages * B_STAGE;
+    const uint32_t off_rowm = off_stg + STG_BYTES;
+    const uint32_t off_bars = off_rowm + 512;
+    float* stg = reinterpret_cast<float*>(smem + off_stg);
+    int* rowm = reinterpret_cast<int*>(smem + off_rowm);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + off_bars);
+    // barrier indices
+    constexpr int I_HF = 0, I_HE = 2, I_BF = 4, I_BE = 4 + MAX_BSTAGES, I_CD = 4 + 2 * MAX_BSTAGES, I_AE = I_CD + A_STAGES,
+                  I_ACCF = I_AE + A_STAGES, I_ACCE = I_ACCF + 1, N_BARS = I_ACCE + 1;
+    auto bar = [&](int i) { return smem_u32(bars + i); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + N_BARS);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cs = t.cs;
+    const uint32_t crank = cs > 1 ? cluster_ctarank() : 0u;
+    const uint16_t cmask = (uint16_t)((1u << cs) - 1u);
+    const int cluster_id = blockIdx.x / cs, num_clusters = gridDim.x / cs;
+    const int total_work = t.m_groups * t.n_tiles;
+    const int BS = t.bstages;
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBhi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBlo) : "memory");
+        for (int s = 0; s < 2; ++s) { mbar_init(bar(I_HF + s), 1); mbar_init(bar(I_HE + s), 128); }
+        for (int s = 0; s < MAX_BSTAGES; ++s) { mbar_init(bar(I_BF + s), 1); mbar_init(bar(I_BE + s), cs); }
+        for (int s = 0; s < A_STAGES; ++s) { mbar_init(bar(I_CD + s), 128); mbar_init(bar(I_AE + s), 1); }
+        mbar_init(bar(I_ACCF), 1);
+        mbar_init(bar(I_ACCE), 128);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS2);
+    tc_fence_before();
+    __syncthreads();
+    if (cs > 1) cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto tile_origin = [&](int work, int& n0, int& oy0, int& ox0) {
+        int m_tile = (work / t.n_tiles) * cs + (int)crank;
+        if (m_tile >= t.m_tiles) { n0 = g.N + 1024; oy0 = 0; ox0 = 0; return; }   // padding CTA of a cluster: everything out of bounds
+        const int tw_i = m_tile % t.tiles_w; m_tile /= t.tiles_w;
+        const int th_i = m_tile % t.tiles_h; m_tile /= t.tiles_h;
+        n0 = m_tile * t.TN; oy0 = th_i * t.TH; ox0 = tw_i * t.TW;
+    };
+
+    if (warp == 0) {
+        // =========================== weight (B) producer ===========================
+        if (lane == 0) {
+            uint32_t bc = 0;
+            const int rows = NT / cs;
+            for (int work = cluster_id; work < total_work; work += num_clusters) {
+                const int nt_i = work % t.n_tiles;
+                for (int cb = 0; cb < t.cblocks; ++cb) {
+                    for (int tap = 0; tap < t.taps; ++tap, ++bc) {
+                        const int s = bc % BS;
+                        const uint32_t ph = (bc / BS) & 1;
+                        mbar_wait(bar(I_BE + s), ph ^ 1);
+                        mbar_expect_tx(bar(I_BF + s), B_STAGE);
+                        const uint32_t dst = smem_base + off_b + s * B_STAGE + crank * rows * 128;
+                        const int row0 = nt_i * NT + (int)crank * rows;
+                        if (cs > 1) {
+                            tma_load_3d_mc(&tmBhi, bar(I_BF + s), dst, cb * KB, row0, tap, cmask);
+                            tma_load_3d_mc(&tmBlo, bar(I_BF + s), dst + B_HALF, cb * KB, row0, tap, cmask);
+                        } else {
+                            tma_load_3d(&tmBhi, bar(I_BF + s), dst, cb * KB, row0, tap);
+                            tma_load_3d(&tmBlo, bar(I_BF + s), dst + B_HALF, cb * KB, row0, tap);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 6) {
+        // =========================== halo (A) producer ===========================
+        if (lane == 0) {
+            uint32_t hc = 0;
+            for (int work = cluster_id; work < total_work; work += num_clusters) {
+                int n0, oy0, ox0;
+                tile_origin(work, n0, oy0, ox0);
+                for (int cb = 0; cb < t.cblocks; ++cb, ++hc) {
+                    const int s = hc & 1;
+                    const uint32_t ph = (hc >> 1) & 1;
+                    mbar_wait(bar(I_HE + s), ph ^ 1);
+                    mbar_expect_tx(bar(I_HF + s), 2u * t.halo_rows * 128u);
+                    const uint32_t dst = smem_base + s * t.halo_stage_bytes;
+                    tma_load_4d(&tmA, bar(I_HF + s), dst, cb * KB, ox0 - t.pw, oy0 - t.ph, n0);
+                    tma_load_4d(&tmA, bar(I_HF + s), dst + t.box_bytes, cb * KB + 32, ox0 - t.pw, oy0 - t.ph, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =========================== MMA issuer ===========================
+        if (lane == 0) {
+            const uint32_t fmt = (t.prec == MN_PREC_BF16X3_TC) ? 1u : 0u;
+            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const bool three = t.prec != MN_PREC_F16X1_TC;
+            const int num_kb = t.cblocks * t.taps;
+            uint32_t bc = 0, ac = 0, tcnt = 0;
+            for (int work = cluster_id; work < total_work; work += num_clusters, ++tcnt) {
+                mbar_wait(bar(I_ACCE), (tcnt & 1) ^ 1);        // epilogue has drained the accumulators of the previous tile
+                tc_fence_after();
+                for (int kb = 0; kb < num_kb; ++kb, ++bc, ++ac) {
+                    const int as = ac % A_STAGES, bs = bc % BS;
+                    mbar_wait(bar(I_CD + as), (ac / A_STAGES) & 1);
+                    mbar_wait(bar(I_BF + bs), (bc / BS) & 1);
+                    tc_fence_after();
+                    const uint32_t b_hi = smem_base + off_b + bs * B_STAGE;
+                    const uint32_t b_lo = b_hi + B_HALF;
+                    const uint32_t a_hi = tmem_base + A_COL0 + as * 64;
+#pragma unroll
+                    for (int j = 0; j < KB / 16; ++j) {
+                        const uint64_t dh = make_b_desc(b_hi + j * 32);
+                        tc_mma_ts(tmem_base, a_hi + j * 8, dh, idesc, (kb | j) != 0);
+                        if (three) {
+                            const uint64_t dl = make_b_desc(b_lo + j * 32);
+                            tc_mma_ts(tmem_base + NT, a_hi + j * 8, dl, idesc, (kb | j) != 0);
+                            tc_mma_ts(tmem_base + NT, a_hi + 32 + j * 8, dh, idesc, 1);
+                        }
+                    }
+                    tc_commit(bar(I_AE + as));
+                    if (cs > 1) tc_commit_mc(bar(I_BE + bs), cmask);
+                    else tc_commit(bar(I_BE + bs));
+                }
+                tc_commit(bar(I_ACCF));
+            }
+        }
+    } else {
+        // =========================== split (fp32 -> hi/lo in TMEM) + epilogue ===========================
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const bool bf = t.prec == MN_PREC_BF16X3_TC;
+        const uint32_t mask = bf ? 0xFFFF0000u : 0xFFFFE000u;
+        const float wscale = t.wscale ? *t.wscale : 1.f;
+        const int tn = r / (t.TH * t.TW);
+        const int rem = r - tn * (t.TH * t.TW);
+        const int th = rem / t.TW, tw = rem - th * t.TW;
+        const int rho0 = (tn * t.HHt + th) * t.HWd + tw;       // halo row of tap (0,0) for this output pixel
+        uint32_t hc = 0, ac = 0, tcnt = 0;
+        for (int work = cluster_id; work < total_work; work += num_clusters, ++tcnt) {
+            const int nt_i = work % t.n_tiles;
+            int n0, oy0, ox0;
+            tile_origin(work, n0, oy0, ox0);
+            {
+                const int n = n0 + tn, oy = oy0 + th, ox = ox0 + tw;
+                rowm[r] = (n < g.N && oy < g.OH && ox < g.OW) ? (n * g.OH + oy) * g.OW + ox : -1;
+            }
+            for (int cb = 0; cb < t.cblocks; ++cb, ++hc) {
+                const int hs = hc & 1;
+                mbar_wait(bar(I_HF + hs), (hc >> 1) & 1);
+                const uint8_t* halo = smem + hs * t.halo_stage_bytes;
+                for (int tap = 0; tap < t.taps; ++tap, ++ac) {
+                    const int as = ac % A_STAGES;
+                    mbar_wait(bar(I_AE + as), ((ac / A_STAGES) & 1) ^ 1);
+                    const int ky = tap / t.KW, kx = tap - ky * t.KW;
+                    const int rho = rho0 + ky * t.HWd + kx;
+                    const uint8_t* a_src = halo + rho * 128;
+                    const int sw = rho & 7;
+                    uint32_t hi[32], lo[32];
+#pragma unroll
+                    for (int box = 0; box < 2; ++box) {
+                        const uint8_t* bsrc = a_src + box * t.box_bytes;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 v = *reinterpret_cast<const float4*>(bsrc + ((j ^ sw) << 4));
+                            const float h0 = __uint_as_float(__float_as_uint(v.x) & mask), h1 = __uint_as_float(__float_as_uint(v.y) & mask);
+                            const float h2 = __uint_as_float(__float_as_uint(v.z) & mask), h3 = __uint_as_float(__float_as_uint(v.w) & mask);
+                            const int c = box * 16 + j * 2;
+                            if (bf) {
+                                hi[c] = pack_bf16(h0, h1); hi[c + 1] = pack_bf16(h2, h3);
+                                lo[c] = pack_bf16(v.x - h0, v.y - h1); lo[c + 1] = pack_bf16(v.z - h2, v.w - h3);
+                            } else {
+                                hi[c] = pack_f16(h0, h1); hi[c + 1] = pack_f16(h2, h3);
+                                lo[c] = pack_f16(v.x - h0, v.y - h1); lo[c + 1] = pack_f16(v.z - h2, v.w - h3);
+                            }
+                        }
+                    }
+                    const uint32_t a_dst = lane_addr + A_COL0 + as * 64;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) tc_st8(a_dst + c * 8, hi + c * 8);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) tc_st8(a_dst + 32 + c * 8, lo + c * 8);
+                    tc_wait_st();
+                    tc_fence_before();
+                    mbar_arrive(bar(I_CD + as));
+                }
+                mbar_arrive(bar(I_HE + hs));         // all 9 taps of this channel block have been read
+            }
+
+            // ---- epilogue: TMEM -> registers -> staging smem -> coalesced global stores ----
+            mbar_wait(bar(I_ACCF), tcnt & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int half = 0; half < NT / STG_COLS; ++half) {
+#pragma unroll
+                for (int chunk = 0; chunk < STG_COLS / 16; ++chunk) {
+                    uint32_t acc[16];
+                    tc_ld16(lane_addr + half * STG_COLS + chunk * 16, acc);
+                    if (t.prec != MN_PREC_F16X1_TC) {
+                        uint32_t cor[16];
+                        tc_ld16(lane_addr + NT + half * STG_COLS + chunk * 16, cor);
+                        tc_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) acc[i] = __float_as_uint((__uint_as_float(acc[i]) + __uint_as_float(cor[i])) * wscale);
+                    } else {
+                        tc_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) acc[i] = __float_as_uint(__uint_as_float(acc[i]) * wscale);
+                    }
+                    float4* dst = reinterpret_cast<float4*>(stg + r * STG_PITCH + chunk * 16);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        dst[i] = make_float4(__uint_as_float(acc[4 * i]), __uint_as_float(acc[4 * i + 1]), __uint_as_float(acc[4 * i + 2]),
+                                             __uint_as_float(acc[4 * i + 3]));
+                }
+                if (half == NT / STG_COLS - 1) {      // accumulators fully read: the MMA warp may start the next tile
+                    tc_fence_before();
+                    mbar_arrive(bar(I_ACCE));
+                }
+                named_bar_sync(1, 128);
+#pragma unroll 4
+                for (int i = 0; i < 16; ++i) {
+                    const int row = q * 32 + i * 2 + (lane >> 4);
+                    const int col = (lane & 15) * 4;
+                    const int m = rowm[row];
+                    const int o = nt_i * NT + half * STG_COLS + col;
+                    if (m >= 0 && o < g.Cout) {
+                        const float4 u = *reinterpret_cast<const float4*>(stg + row * STG_PITCH + col);
+                        float v[4] = {u.x, u.y, u.z, u.w};
+                        conv_epilogue4(g, m, o, v);
+                    }
+                }
+                named_bar_sync(1, 128);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (cs > 1) cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS2);
+    }
+}
+
+// ------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled get_encode2() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+struct Tc2Plan { bool ok; const char* why; int NT; int smem; Tc2Geom t; };
+
+bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+Tc2Plan plan_tc2(const ConvGeom& g) {
+    Tc2Plan p{};
+    auto fail = [&](const char* w) { p.ok = false; p.why = w; return p; };
+    if (g.sh != 1 || g.sw != 1) return fail("stride != 1");
+    const bool k3 = g.KH == 3 && g.KW == 3 && g.ph == 1 && g.pw == 1, k1 = g.KH == 1 && g.KW == 1 && g.ph == 0 && g.pw == 0;
+    if (!k3 && !k1) return fail("only 3x3/pad1 and 1x1/pad0");
+    if (g.Cin % KB != 0) return fail("Cin % 64 != 0");
+    if (g.Cout % 64 != 0) return fail("Cout % 64 != 0");
+    if (g.x_cs % 4 != 0 || (reinterpret_cast<uintptr_t>(g.x) & 15)) return fail("x alignment");
+    Tc2Geom& t = p.t;
+    t.TH = g.H < 8 ? g.H : 8;
+    if (!is_pow2(t.TH) || g.H % t.TH) return fail("H must be a multiple of 8 (or a power of two below 8)");
+    const int maxw = 128 / t.TH;
+    t.TW = g.W < maxw ? g.W : maxw;
+    if (!is_pow2(t.TW) || g.W % t.TW) return fail("W must be a multiple of 128/TH (or a power of two below it)");
+    t.TN = 128 / (t.TH * t.TW);
+    t.ph = g.ph; t.pw = g.pw; t.KW = g.KW;
+    t.HHt = t.TH + 2 * g.ph; t.HWd = t.TW + 2 * g.pw;
+    t.halo_rows = t.TN * t.HHt * t.HWd;
+    if (t.halo_rows > 208) return fail("halo tile too large for shared memory (tiny images: use the split-K fp32 path)");
+    if (t.HWd > 256 || t.HHt > 256 || t.TN > 256) return fail("TMA box dim");
+    t.box_bytes = (t.halo_rows * 128 + 1023) & ~1023;
+    t.halo_stage_bytes = 2 * t.box_bytes;
+    t.tiles_w = g.W / t.TW; t.tiles_h = g.H / t.TH; t.tiles_n = (g.N + t.TN - 1) / t.TN;
+    t.m_tiles = t.tiles_w * t.tiles_h * t.tiles_n;
+    t.cblocks = g.Cin / KB; t.taps = g.KH * g.KW;
+    p.NT = (g.Cout % 128 == 0) ? 128 : 64;
+    t.n_tiles = g.Cout / p.NT;
+    static int force_cs = -1;
+    if (force_cs < 0) { const char* e = getenv("MN_TC_CLUSTER"); force_cs = e ? atoi(e) : 0; }
+    t.cs = force_cs > 0 ? force_cs : (t.m_tiles >= 2 ? 2 : 1);
+    if (t.cs != 1 && t.cs != 2 && t.cs != 4) t.cs = 1;
+    if ((p.NT / t.cs) % 8 != 0) t.cs = 1;
+    t.m_groups = (t.m_tiles + t.cs - 1) / t.cs;
+    const int fixed = 2 * t.halo_stage_bytes + STG_BYTES + 512 + 256 + 1024;
+    int bs = (SMEM_LIMIT - fixed) / (2 * p.NT * 128);
+    if (bs > MAX_BSTAGES) bs = MAX_BSTAGES;
+    if (bs < 2) return fail("not enough shared memory for 2 weight stages");
+    t.bstages = bs;
+    p.smem = fixed + bs * 2 * p.NT * 128;
+    p.ok = true;
+    return p;
+}
+
+template <int NT>
+int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mbh, const CUtensorMap& mbl, const ConvGeom& g, const Tc2Plan& p, cudaStream_t st) {
+    static int smem_set = 0;
+    if (smem_set < p.smem) {
+        MN_CUDA_CHECK(cudaFuncSetAttribute(conv_tc2_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        smem_set = SMEM_LIMIT;
+    }
+    const Tc2Geom& t = p.t;
+    const int total_work = t.m_groups * t.n_tiles;
+    int clusters = mn_num_sms() / t.cs;
+    if (clusters > total_work) clusters = total_work;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(clusters * t.cs, 1, 1);
+    cfg.blockDim = dim3(NUM_THREADS2, 1, 1);
+    cfg.dynamicSmemBytes = p.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = t.cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    MN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<NT>, ma, mbh, mbl, g, t));
+    return MN_OK;
+}
+
+}  // namespace
+
+int mn_conv_tc2_supported(const ConvGeom& g, const char** why) {
+    Tc2Plan p = plan_tc2(g);
+    if (why) *why = p.ok ? "" : p.why;
+    return p.ok ? 1 : 0;
+}
+
+int mn_conv_tc2_launch(const ConvGeom& g, const void* w_hi, const void* w_lo, const float* w_scale, int prec, cudaStream_t st) {
+    Tc2Plan p = plan_tc2(g);
+    if (!p.ok) { mn_set_error("mn_conv2d_nhwc: tcgen05 v2 path does not support this shape (%s)", p.why); return MN_ERR_UNSUPPORTED; }
+    if (!w_hi || !w_lo || !w_scale) { mn_set_error("mn_conv2d_nhwc: tensor-core precision needs packed w_tc_hi/w_tc_lo/w_tc_scale"); return MN_ERR_INVALID; }
+    PFN_encodeTiled enc = get_encode2();
+    if (!enc) { mn_set_error("cuTensorMapEncodeTiled not available from the driver"); return MN_ERR_CUDA; }
+    CUtensorMap ma, mbh, mbl;
+    Tc2Geom& t = p.t;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)g.Cin, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.N};
+        cuuint64_t strides[3] = {(cuuint64_t)g.x_cs * 4, (cuuint64_t)g.W * g.x_cs * 4, (cuuint64_t)g.H * g.W * g.x_cs * 4};
+        cuuint32_t box[4] = {32, (cuuint32_t)t.HWd, (cuuint32_t)t.HHt, (cuuint32_t)t.TN};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult r = enc(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(g.x), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { mn_set_error("cuTensorMapEncodeTiled(A halo) failed: %d", (int)r); return MN_ERR_CUDA; }
+    }
+    const CUtensorMapDataType dt = (prec == MN_PREC_BF16X3_TC) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    for (int which = 0; which < 2; ++which) {
+        cuuint64_t dims[3] = {(cuuint64_t)g.Cin, (cuuint64_t)g.Cout, (cuuint64_t)(g.KH * g.KW)};
+        cuuint64_t strides[2] = {(cuuint64_t)g.Cin * 2, (cuuint64_t)g.Cin * g.Cout * 2};
+        cuuint32_t box[3] = {64, (cuuint32_t)(p.NT / t.cs), 1};
+        cuuint32_t es[3] = {1, 1, 1};
+        CUresult r = enc(which ? &mbl : &mbh, dt, 3, const_cast<void*>(which ? w_lo : w_hi), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { mn_set_error("cuTensorMapEncodeTiled(B) failed: %d", (int)r); return MN_ERR_CUDA; }
+    }
+    t.wscale = w_scale + 1;
+    t.prec = prec;
+    return p.NT == 128 ? launch_tc2<128>(ma, mbh, mbl, g, p, st) : launch_tc2<64>(ma, mbh, mbl, g, p, st);
+}

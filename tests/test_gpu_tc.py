@@ -45,6 +45,9 @@ TC_CASES = [
     (2, 16, 128, 256, 128, 1),    # 1x1
     (1, 32, 32, 512, 512, 3),     # deep K: 72 k-blocks, many pipeline wraps
     (70, 1, 1, 512, 1024, 1),     # a linear layer: [M,1,1,K]
+    (3, 8, 16, 64, 128, 3),       # odd number of pixel tiles: padding CTA inside a 2-CTA cluster
+    (1, 64, 1024, 64, 64, 3),     # 512 pixel tiles: several work items per persistent CTA
+    (1, 16, 512, 128, 256, 1),    # 1x1 on a wide map, two N tiles
 ]
 # tensor-core fp32 accumulation truncates (round-toward-zero): the error grows ~linearly with K/16 accumulation steps
 TOL = {"f16x3": 4e-5, "bf16x3": 2e-4, "f16x1": 4e-3}
