@@ -12,7 +12,12 @@
 //     every weight tile and TMA-multicast it to all; the stage is released by tcgen05.commit multicast to every CTA.
 //   * PERSISTENT tiles: one CTA per SM loops over work items; producers run ahead into the next tile while the split
 //     warps drain TMEM (through a shared-memory staging buffer -> fully coalesced global stores).
-// Warp roles: 0 = weight (B) TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = split + epilogue, 6 = halo TMA producer.
+//   * SPLIT ONCE.  fp32->fp16 pair conversion (F2FP) runs on the quarter-rate XU pipe; converting every tap's tile costs
+//     ~1000 XU cycles per 768-cycle MMA block (measured: XU 53 % busy, tensor pipe 12 %).  Four dedicated warps now split
+//     each halo tile ONCE per channel block, in place in shared memory (hi plane over box 0, lo plane over box 1, same
+//     XOR swizzle), and the four TMEM-feeding warps only copy shifted rows smem -> TMEM per tap (no ALU work).
+// Warp roles: 0 = weight (B) TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = TMEM feed + epilogue,
+//             6 = halo TMA producer, 7..10 = split (fp32 halo -> hi/lo fp16 halo).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -26,7 +31,7 @@ namespace {
 using namespace tcptx;
 
 constexpr int KB = 64;
-constexpr int NUM_THREADS2 = 224;
+constexpr int NUM_THREADS2 = 352;
 constexpr int A_STAGES = 3;
 constexpr int MAX_BSTAGES = 4;
 constexpr int STG_COLS = 64;
@@ -65,7 +70,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + off_bars);
     // barrier indices
     constexpr int I_HF = 0, I_HE = 2, I_BF = 4, I_BE = 4 + MAX_BSTAGES, I_CD = 4 + 2 * MAX_BSTAGES, I_AE = I_CD + A_STAGES,
-                  I_ACCF = I_AE + A_STAGES, I_ACCE = I_ACCF + 1, N_BARS = I_ACCE + 1;
+                  I_ACCF = I_AE + A_STAGES, I_ACCE = I_ACCF + 1, I_SD = I_ACCE + 1, N_BARS = I_SD + 2;
     auto bar = [&](int i) { return smem_u32(bars + i); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + N_BARS);
 
@@ -81,7 +86,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBhi) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBlo) : "memory");
-        for (int s = 0; s < 2; ++s) { mbar_init(bar(I_HF + s), 1); mbar_init(bar(I_HE + s), 128); }
+        for (int s = 0; s < 2; ++s) { mbar_init(bar(I_HF + s), 1); mbar_init(bar(I_HE + s), 128); mbar_init(bar(I_SD + s), 128); }
         for (int s = 0; s < MAX_BSTAGES; ++s) { mbar_init(bar(I_BF + s), 1); mbar_init(bar(I_BE + s), cs); }
         for (int s = 0; s < A_STAGES; ++s) { mbar_init(bar(I_CD + s), 128); mbar_init(bar(I_AE + s), 1); }
         mbar_init(bar(I_ACCF), 1);
@@ -147,6 +152,51 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 }
             }
         }
+    } else if (warp >= 7) {
+        // =========================== split warps: fp32 halo -> (hi, lo) 16-bit halo, in place ===========================
+        const int sidx = (warp - 7) * 32 + lane;
+        const bool bf = t.prec == MN_PREC_BF16X3_TC;
+        const uint32_t mask = bf ? 0xFFFF0000u : 0xFFFFE000u;
+        uint32_t hc = 0;
+        for (int work = cluster_id; work < total_work; work += num_clusters) {
+            for (int cb = 0; cb < t.cblocks; ++cb, ++hc) {
+                const int hs = hc & 1;
+                mbar_wait(bar(I_HF + hs), (hc >> 1) & 1);
+                uint8_t* halo = smem + hs * t.halo_stage_bytes;
+                for (int rho = sidx; rho < t.halo_rows; rho += 128) {
+                    uint8_t* row0 = halo + rho * 128;
+                    uint8_t* row1 = row0 + t.box_bytes;
+                    const int sw = rho & 7;
+                    uint32_t hi[32], lo[32];
+#pragma unroll
+                    for (int box = 0; box < 2; ++box) {
+                        const uint8_t* bsrc = box ? row1 : row0;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 v = *reinterpret_cast<const float4*>(bsrc + ((j ^ sw) << 4));
+                            const float h0 = __uint_as_float(__float_as_uint(v.x) & mask), h1 = __uint_as_float(__float_as_uint(v.y) & mask);
+                            const float h2 = __uint_as_float(__float_as_uint(v.z) & mask), h3 = __uint_as_float(__float_as_uint(v.w) & mask);
+                            const int c = box * 16 + j * 2;
+                            if (bf) {
+                                hi[c] = pack_bf16(h0, h1); hi[c + 1] = pack_bf16(h2, h3);
+                                lo[c] = pack_bf16(v.x - h0, v.y - h1); lo[c + 1] = pack_bf16(v.z - h2, v.w - h3);
+                            } else {
+                                hi[c] = pack_f16(h0, h1); hi[c + 1] = pack_f16(h2, h3);
+                                lo[c] = pack_f16(v.x - h0, v.y - h1); lo[c + 1] = pack_f16(v.z - h2, v.w - h3);
+                            }
+                        }
+                    }
+                    // all 256 B of this row are in registers now: overwrite it (row0 <- hi plane, row1 <- lo plane)
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) {
+                        *reinterpret_cast<uint4*>(row0 + ((jj ^ sw) << 4)) = make_uint4(hi[4 * jj], hi[4 * jj + 1], hi[4 * jj + 2], hi[4 * jj + 3]);
+                        *reinterpret_cast<uint4*>(row1 + ((jj ^ sw) << 4)) = make_uint4(lo[4 * jj], lo[4 * jj + 1], lo[4 * jj + 2], lo[4 * jj + 3]);
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // these generic writes precede the next TMA refill
+                mbar_arrive(bar(I_SD + hs));
+            }
+        }
     } else if (warp == 1) {
         // =========================== MMA issuer ===========================
         if (lane == 0) {
@@ -184,12 +234,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
         }
     } else {
-        // =========================== split (fp32 -> hi/lo in TMEM) + epilogue ===========================
+        // =========================== TMEM feed (shifted rows of the split halo -> A operand) + epilogue ===========================
         const int q = warp & 3;
         const int r = q * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-        const bool bf = t.prec == MN_PREC_BF16X3_TC;
-        const uint32_t mask = bf ? 0xFFFF0000u : 0xFFFFE000u;
         const float wscale = t.wscale ? *t.wscale : 1.f;
         const int tn = r / (t.TH * t.TW);
         const int rem = r - tn * (t.TH * t.TW);
@@ -206,34 +254,25 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
             for (int cb = 0; cb < t.cblocks; ++cb, ++hc) {
                 const int hs = hc & 1;
-                mbar_wait(bar(I_HF + hs), (hc >> 1) & 1);
+                mbar_wait(bar(I_SD + hs), (hc >> 1) & 1);
                 const uint8_t* halo = smem + hs * t.halo_stage_bytes;
                 for (int tap = 0; tap < t.taps; ++tap, ++ac) {
                     const int as = ac % A_STAGES;
-                    mbar_wait(bar(I_AE + as), ((ac / A_STAGES) & 1) ^ 1);
                     const int ky = tap / t.KW, kx = tap - ky * t.KW;
                     const int rho = rho0 + ky * t.HWd + kx;
-                    const uint8_t* a_src = halo + rho * 128;
+                    const uint8_t* hsrc = halo + rho * 128;
+                    const uint8_t* lsrc = hsrc + t.box_bytes;
                     const int sw = rho & 7;
                     uint32_t hi[32], lo[32];
 #pragma unroll
-                    for (int box = 0; box < 2; ++box) {
-                        const uint8_t* bsrc = a_src + box * t.box_bytes;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 v = *reinterpret_cast<const float4*>(bsrc + ((j ^ sw) << 4));
-                            const float h0 = __uint_as_float(__float_as_uint(v.x) & mask), h1 = __uint_as_float(__float_as_uint(v.y) & mask);
-                            const float h2 = __uint_as_float(__float_as_uint(v.z) & mask), h3 = __uint_as_float(__float_as_uint(v.w) & mask);
-                            const int c = box * 16 + j * 2;
-                            if (bf) {
-                                hi[c] = pack_bf16(h0, h1); hi[c + 1] = pack_bf16(h2, h3);
-                                lo[c] = pack_bf16(v.x - h0, v.y - h1); lo[c + 1] = pack_bf16(v.z - h2, v.w - h3);
-                            } else {
-                                hi[c] = pack_f16(h0, h1); hi[c + 1] = pack_f16(h2, h3);
-                                lo[c] = pack_f16(v.x - h0, v.y - h1); lo[c + 1] = pack_f16(v.z - h2, v.w - h3);
-                            }
-                        }
+                    for (int jj = 0; jj < 8; ++jj) {
+                        const uint4 a = *reinterpret_cast<const uint4*>(hsrc + ((jj ^ sw) << 4));
+                        const uint4 b = *reinterpret_cast<const uint4*>(lsrc + ((jj ^ sw) << 4));
+                        hi[4 * jj] = a.x; hi[4 * jj + 1] = a.y; hi[4 * jj + 2] = a.z; hi[4 * jj + 3] = a.w;
+                        lo[4 * jj] = b.x; lo[4 * jj + 1] = b.y; lo[4 * jj + 2] = b.z; lo[4 * jj + 3] = b.w;
                     }
+                    mbar_wait(bar(I_AE + as), ((ac / A_STAGES) & 1) ^ 1);
+                    tc_fence_after();
                     const uint32_t a_dst = lane_addr + A_COL0 + as * 64;
 #pragma unroll
                     for (int c = 0; c < 4; ++c) tc_st8(a_dst + c * 8, hi + c * 8);
@@ -243,7 +282,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     tc_fence_before();
                     mbar_arrive(bar(I_CD + as));
                 }
-                mbar_arrive(bar(I_HE + hs));         // all 9 taps of this channel block have been read
+                mbar_arrive(bar(I_HE + hs));         // all taps of this channel block have been read
             }
 
             // ---- epilogue: TMEM -> registers -> staging smem -> coalesced global stores ----
