@@ -109,20 +109,18 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     };
 
     if (warp == 0) {
-        // =========================== weight (B) producer ===========================
-        if (lane == 0) {
-            uint32_t bc = 0;
-            const int rows = NT / cs;
-            for (int work = cluster_id; work < total_work; work += num_clusters) {
-                const int nt_i = work % t.n_tiles;
-                for (int cb = 0; cb < t.cblocks; ++cb) {
-                    for (int tap = 0; tap < t.taps; ++tap, ++bc) {
-                        const int s = bc % BS;
-                        const uint32_t ph = (bc / BS) & 1;
-                        mbar_wait(bar(I_BE + s), ph ^ 1);
+        // =========================== weight (B) producer (whole warp converged, one elected lane issues) ===========================
+        uint32_t s = 0, ph = 0;
+        const int rows = NT / cs;
+        const uint32_t dst0 = smem_base + off_b + crank * rows * 128;
+        for (int work = cluster_id; work < total_work; work += num_clusters) {
+            const int row0 = (work % t.n_tiles) * NT + (int)crank * rows;
+            for (int cb = 0; cb < t.cblocks; ++cb) {
+                for (int tap = 0; tap < t.taps; ++tap) {
+                    mbar_wait(bar(I_BE + s), ph ^ 1);
+                    if (elect_one_sync()) {
                         mbar_expect_tx(bar(I_BF + s), B_STAGE);
-                        const uint32_t dst = smem_base + off_b + s * B_STAGE + crank * rows * 128;
-                        const int row0 = nt_i * NT + (int)crank * rows;
+                        const uint32_t dst = dst0 + s * B_STAGE;
                         if (cs > 1) {
                             tma_load_3d_mc(&tmBhi, bar(I_BF + s), dst, cb * KB, row0, tap, cmask);
                             tma_load_3d_mc(&tmBlo, bar(I_BF + s), dst + B_HALF, cb * KB, row0, tap, cmask);
@@ -131,25 +129,27 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             tma_load_3d(&tmBlo, bar(I_BF + s), dst + B_HALF, cb * KB, row0, tap);
                         }
                     }
+                    __syncwarp();
+                    if (++s == (uint32_t)BS) { s = 0; ph ^= 1; }
                 }
             }
         }
     } else if (warp == 6) {
         // =========================== halo (A) producer ===========================
-        if (lane == 0) {
-            uint32_t hc = 0;
-            for (int work = cluster_id; work < total_work; work += num_clusters) {
-                int n0, oy0, ox0;
-                tile_origin(work, n0, oy0, ox0);
-                for (int cb = 0; cb < t.cblocks; ++cb, ++hc) {
-                    const int s = hc & 1;
-                    const uint32_t ph = (hc >> 1) & 1;
-                    mbar_wait(bar(I_HE + s), ph ^ 1);
-                    mbar_expect_tx(bar(I_HF + s), 2u * t.halo_rows * 128u);
-                    const uint32_t dst = smem_base + s * t.halo_stage_bytes;
-                    tma_load_4d(&tmA, bar(I_HF + s), dst, cb * KB, ox0 - t.pw, oy0 - t.ph, n0);
-                    tma_load_4d(&tmA, bar(I_HF + s), dst + t.box_bytes, cb * KB + 32, ox0 - t.pw, oy0 - t.ph, n0);
+        uint32_t hs = 0, ph = 0;
+        for (int work = cluster_id; work < total_work; work += num_clusters) {
+            int n0, oy0, ox0;
+            tile_origin(work, n0, oy0, ox0);
+            for (int cb = 0; cb < t.cblocks; ++cb) {
+                mbar_wait(bar(I_HE + hs), ph ^ 1);
+                if (elect_one_sync()) {
+                    mbar_expect_tx(bar(I_HF + hs), 2u * t.halo_rows * 128u);
+                    const uint32_t dst = smem_base + hs * t.halo_stage_bytes;
+                    tma_load_4d(&tmA, bar(I_HF + hs), dst, cb * KB, ox0 - t.pw, oy0 - t.ph, n0);
+                    tma_load_4d(&tmA, bar(I_HF + hs), dst + t.box_bytes, cb * KB + 32, ox0 - t.pw, oy0 - t.ph, n0);
                 }
+                __syncwarp();
+                hs ^= 1; if (hs == 0) ph ^= 1;
             }
         }
     } else if (warp >= 7) {
@@ -157,11 +157,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int sidx = (warp - 7) * 32 + lane;
         const bool bf = t.prec == MN_PREC_BF16X3_TC;
         const uint32_t mask = bf ? 0xFFFF0000u : 0xFFFFE000u;
-        uint32_t hc = 0;
+        uint32_t hs = 0, hph = 0;
         for (int work = cluster_id; work < total_work; work += num_clusters) {
-            for (int cb = 0; cb < t.cblocks; ++cb, ++hc) {
-                const int hs = hc & 1;
-                mbar_wait(bar(I_HF + hs), (hc >> 1) & 1);
+            for (int cb = 0; cb < t.cblocks; ++cb) {
+                mbar_wait(bar(I_HF + hs), hph);
                 uint8_t* halo = smem + hs * t.halo_stage_bytes;
                 for (int rho = sidx; rho < t.halo_rows; rho += 128) {
                     uint8_t* row0 = halo + rho * 128;
@@ -195,43 +194,46 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // these generic writes precede the next TMA refill
                 mbar_arrive(bar(I_SD + hs));
+                hs ^= 1; if (hs == 0) hph ^= 1;
             }
         }
     } else if (warp == 1) {
-        // =========================== MMA issuer ===========================
-        if (lane == 0) {
-            const uint32_t fmt = (t.prec == MN_PREC_BF16X3_TC) ? 1u : 0u;
-            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            const bool three = t.prec != MN_PREC_F16X1_TC;
-            const int num_kb = t.cblocks * t.taps;
-            uint32_t bc = 0, ac = 0, tcnt = 0;
-            for (int work = cluster_id; work < total_work; work += num_clusters, ++tcnt) {
-                mbar_wait(bar(I_ACCE), (tcnt & 1) ^ 1);        // epilogue has drained the accumulators of the previous tile
+        // =========================== MMA issuer (whole warp converged, one elected lane issues) ===========================
+        const uint32_t fmt = (t.prec == MN_PREC_BF16X3_TC) ? 1u : 0u;
+        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const bool three = t.prec != MN_PREC_F16X1_TC;
+        const int num_kb = t.cblocks * t.taps;
+        const uint64_t desc_hi0 = make_b_desc(smem_base + off_b);           // stage 0, hi plane, k-step 0
+        uint32_t as = 0, aph = 0, bs = 0, bph = 0, tcnt = 0;
+        for (int work = cluster_id; work < total_work; work += num_clusters, ++tcnt) {
+            mbar_wait(bar(I_ACCE), (tcnt & 1) ^ 1);        // epilogue has drained the accumulators of the previous tile
+            tc_fence_after();
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(bar(I_CD + as), aph);
+                mbar_wait(bar(I_BF + bs), bph);
                 tc_fence_after();
-                for (int kb = 0; kb < num_kb; ++kb, ++bc, ++ac) {
-                    const int as = ac % A_STAGES, bs = bc % BS;
-                    mbar_wait(bar(I_CD + as), (ac / A_STAGES) & 1);
-                    mbar_wait(bar(I_BF + bs), (bc / BS) & 1);
-                    tc_fence_after();
-                    const uint32_t b_hi = smem_base + off_b + bs * B_STAGE;
-                    const uint32_t b_lo = b_hi + B_HALF;
+                if (elect_one_sync()) {
+                    const uint64_t dh0 = desc_hi0 + (uint64_t)((bs * B_STAGE) >> 4);   // start-address field is in 16-byte units
+                    const uint64_t dl0 = dh0 + (uint64_t)(B_HALF >> 4);
                     const uint32_t a_hi = tmem_base + A_COL0 + as * 64;
 #pragma unroll
                     for (int j = 0; j < KB / 16; ++j) {
-                        const uint64_t dh = make_b_desc(b_hi + j * 32);
-                        tc_mma_ts(tmem_base, a_hi + j * 8, dh, idesc, (kb | j) != 0);
+                        tc_mma_ts(tmem_base, a_hi + j * 8, dh0 + 2 * j, idesc, (kb | j) != 0);
                         if (three) {
-                            const uint64_t dl = make_b_desc(b_lo + j * 32);
-                            tc_mma_ts(tmem_base + NT, a_hi + j * 8, dl, idesc, (kb | j) != 0);
-                            tc_mma_ts(tmem_base + NT, a_hi + 32 + j * 8, dh, idesc, 1);
+                            tc_mma_ts(tmem_base + NT, a_hi + j * 8, dl0 + 2 * j, idesc, (kb | j) != 0);
+                            tc_mma_ts(tmem_base + NT, a_hi + 32 + j * 8, dh0 + 2 * j, idesc, 1);
                         }
                     }
                     tc_commit(bar(I_AE + as));
                     if (cs > 1) tc_commit_mc(bar(I_BE + bs), cmask);
                     else tc_commit(bar(I_BE + bs));
                 }
-                tc_commit(bar(I_ACCF));
+                __syncwarp();
+                if (++as == A_STAGES) { as = 0; aph ^= 1; }
+                if (++bs == (uint32_t)BS) { bs = 0; bph ^= 1; }
             }
+            if (elect_one_sync()) tc_commit(bar(I_ACCF));
+            __syncwarp();
         }
     } else {
         // =========================== TMEM feed (shifted rows of the split halo -> A operand) + epilogue ===========================
@@ -243,7 +245,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int rem = r - tn * (t.TH * t.TW);
         const int th = rem / t.TW, tw = rem - th * t.TW;
         const int rho0 = (tn * t.HHt + th) * t.HWd + tw;       // halo row of tap (0,0) for this output pixel
-        uint32_t hc = 0, ac = 0, tcnt = 0;
+        uint32_t hs = 0, hph = 0, as = 0, aph = 0, tcnt = 0;
         for (int work = cluster_id; work < total_work; work += num_clusters, ++tcnt) {
             const int nt_i = work % t.n_tiles;
             int n0, oy0, ox0;
@@ -252,14 +254,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const int n = n0 + tn, oy = oy0 + th, ox = ox0 + tw;
                 rowm[r] = (n < g.N && oy < g.OH && ox < g.OW) ? (n * g.OH + oy) * g.OW + ox : -1;
             }
-            for (int cb = 0; cb < t.cblocks; ++cb, ++hc) {
-                const int hs = hc & 1;
-                mbar_wait(bar(I_SD + hs), (hc >> 1) & 1);
+            for (int cb = 0; cb < t.cblocks; ++cb) {
+                mbar_wait(bar(I_SD + hs), hph);
                 const uint8_t* halo = smem + hs * t.halo_stage_bytes;
-                for (int tap = 0; tap < t.taps; ++tap, ++ac) {
-                    const int as = ac % A_STAGES;
-                    const int ky = tap / t.KW, kx = tap - ky * t.KW;
+                int ky = 0, kx = 0;
+                for (int tap = 0; tap < t.taps; ++tap) {
                     const int rho = rho0 + ky * t.HWd + kx;
+                    if (++kx == t.KW) { kx = 0; ++ky; }
                     const uint8_t* hsrc = halo + rho * 128;
                     const uint8_t* lsrc = hsrc + t.box_bytes;
                     const int sw = rho & 7;
@@ -271,7 +272,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         hi[4 * jj] = a.x; hi[4 * jj + 1] = a.y; hi[4 * jj + 2] = a.z; hi[4 * jj + 3] = a.w;
                         lo[4 * jj] = b.x; lo[4 * jj + 1] = b.y; lo[4 * jj + 2] = b.z; lo[4 * jj + 3] = b.w;
                     }
-                    mbar_wait(bar(I_AE + as), ((ac / A_STAGES) & 1) ^ 1);
+                    mbar_wait(bar(I_AE + as), aph ^ 1);
                     tc_fence_after();
                     const uint32_t a_dst = lane_addr + A_COL0 + as * 64;
 #pragma unroll
@@ -281,8 +282,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     tc_wait_st();
                     tc_fence_before();
                     mbar_arrive(bar(I_CD + as));
+                    if (++as == A_STAGES) { as = 0; aph ^= 1; }
                 }
                 mbar_arrive(bar(I_HE + hs));         // all taps of this channel block have been read
+                hs ^= 1; if (hs == 0) hph ^= 1;
             }
 
             // ---- epilogue: TMEM -> registers -> staging smem -> coalesced global stores ----

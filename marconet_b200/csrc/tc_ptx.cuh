@@ -106,6 +106,21 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo_elem, float hi_elem) {
 }
 
 
+// One elected lane of a fully converged warp (CUTLASS idiom).  Code under `if (elect_one_sync())` inside warp-uniform
+// control flow lets ptxas feed tcgen05/TMA uniform-register operands with plain R2UR instead of the
+// ELECT + R2UR.BROADCAST + BRA.U.ANY loop it emits under a divergent `lane == 0` branch.
+__device__ __forceinline__ uint32_t elect_one_sync() {
+    uint32_t pred = 0, laneid = 0;
+    asm volatile(
+        "{\n\t.reg .b32 %%rx;\n\t.reg .pred %%px;\n\t"
+        "elect.sync %%rx|%%px, %2;\n\t"
+        "@%%px mov.s32 %1, 1;\n\t"
+        "mov.s32 %0, %%rx;\n\t}"
+        : "+r"(laneid), "+r"(pred)
+        : "r"(0xFFFFFFFFu));
+    return pred;
+}
+
 // ---- cluster / multicast variants ----
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
