@@ -56,6 +56,35 @@ __device__ __forceinline__ void conv_epilogue4(const ConvGeom& g, int m, int o, 
     }
 }
 
+// Vectorised epilogue for the tensor-core kernels: 4 consecutive channels [o,o+4) (o % 4 == 0, Cout % 4 == 0) of pixel m
+// belonging to sample n; float4 loads of the per-channel / per-sample vectors, no integer division.
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void conv_epilogue_vec4(const ConvGeom& g, int m, int n, bool masked, int o, float4 v, float4 bias4) {
+    if (g.out_scale) {
+        const float4 s = ldg4(g.out_scale + (size_t)n * g.os_stride + o);
+        v.x *= s.x; v.y *= s.y; v.z *= s.z; v.w *= s.w;
+    }
+    v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+    if (g.residual) {
+        const size_t rm = g.res_bcast ? (size_t)(m - n * g.OH * g.OW) : (size_t)m;
+        const float4 r = ldg4(g.residual + rm * g.res_cs + o);
+        v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+    }
+    if (g.act != MN_ACT_NONE) {
+        v.x = mn_apply_act(v.x, g.act); v.y = mn_apply_act(v.y, g.act); v.z = mn_apply_act(v.z, g.act); v.w = mn_apply_act(v.w, g.act);
+    }
+    v.x *= g.gain; v.y *= g.gain; v.z *= g.gain; v.w *= g.gain;
+    if (masked) v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g.y) *reinterpret_cast<float4*>(g.y + (size_t)m * g.y_cs + o) = v;
+    if (g.y2) {
+        if (g.y2_scale) {
+            const float4 s = ldg4(g.y2_scale + (size_t)n * g.y2s_stride + o);
+            v.x *= s.x; v.y *= s.y; v.z *= s.z; v.w *= s.w;
+        }
+        *reinterpret_cast<float4*>(g.y2 + (size_t)m * g.y2_cs + o) = v;
+    }
+}
+
 int mn_conv_simt_plan_splits(const ConvGeom& g, int64_t ws_bytes, int requested);
 int mn_conv_simt_launch(ConvGeom g, const float* unused, cudaStream_t st);
 

@@ -32,7 +32,7 @@ using namespace tcptx;
 
 constexpr int KB = 64;
 constexpr int NUM_THREADS2 = 352;
-constexpr int A_STAGES = 3;
+constexpr int A_STAGES = 4;
 constexpr int MAX_BSTAGES = 4;
 constexpr int STG_COLS = 64;
 constexpr int STG_PITCH = STG_COLS + 4;
@@ -64,7 +64,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t off_b = 2 * t.halo_stage_bytes;
     const uint32_t off_stg = off_b + t.bstages * B_STAGE;
     const uint32_t off_rowm = off_stg + STG_BYTES;
-    const uint32_t off_bars = off_rowm + 512;
+    const uint32_t off_bars = off_rowm + 1024;
     float* stg = reinterpret_cast<float*>(smem + off_stg);
     int* rowm = reinterpret_cast<int*>(smem + off_rowm);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + off_bars);
@@ -252,7 +252,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             tile_origin(work, n0, oy0, ox0);
             {
                 const int n = n0 + tn, oy = oy0 + th, ox = ox0 + tw;
-                rowm[r] = (n < g.N && oy < g.OH && ox < g.OW) ? (n * g.OH + oy) * g.OW + ox : -1;
+                const bool ok = n < g.N && oy < g.OH && ox < g.OW;
+                rowm[r] = ok ? (n * g.OH + oy) * g.OW + ox : -1;
+                rowm[128 + r] = ok ? (n | ((g.valid_w && ox >= g.valid_w[n]) ? (1 << 30) : 0)) : 0;
             }
             for (int cb = 0; cb < t.cblocks; ++cb) {
                 mbar_wait(bar(I_SD + hs), hph);
@@ -319,16 +321,19 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     mbar_arrive(bar(I_ACCE));
                 }
                 named_bar_sync(1, 128);
-#pragma unroll 4
-                for (int i = 0; i < 16; ++i) {
-                    const int row = q * 32 + i * 2 + (lane >> 4);
+                {
                     const int col = (lane & 15) * 4;
-                    const int m = rowm[row];
                     const int o = nt_i * NT + half * STG_COLS + col;
-                    if (m >= 0 && o < g.Cout) {
-                        const float4 u = *reinterpret_cast<const float4*>(stg + row * STG_PITCH + col);
-                        float v[4] = {u.x, u.y, u.z, u.w};
-                        conv_epilogue4(g, m, o, v);
+                    const float4 bias4 = g.bias ? ldg4(g.bias + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+                    for (int i = 0; i < 16; ++i) {
+                        const int row = q * 32 + i * 2 + (lane >> 4);
+                        const int m = rowm[row];
+                        if (m >= 0) {
+                            const int nn = rowm[128 + row];
+                            const float4 u = *reinterpret_cast<const float4*>(stg + row * STG_PITCH + col);
+                            conv_epilogue_vec4(g, m, nn & 0x3FFFFFFF, (nn >> 30) != 0, o, u, bias4);
+                        }
                     }
                 }
                 named_bar_sync(1, 128);
@@ -372,6 +377,11 @@ Tc2Plan plan_tc2(const ConvGeom& g) {
     if (g.Cin % KB != 0) return fail("Cin % 64 != 0");
     if (g.Cout % 64 != 0) return fail("Cout % 64 != 0");
     if (g.x_cs % 4 != 0 || (reinterpret_cast<uintptr_t>(g.x) & 15)) return fail("x alignment");
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    if ((g.y && (g.y_cs % 4 || !al16(g.y))) || (g.y2 && (g.y2_cs % 4 || !al16(g.y2))) || (g.residual && (g.res_cs % 4 || !al16(g.residual))) ||
+        (g.out_scale && (g.os_stride % 4 || !al16(g.out_scale))) || (g.y2_scale && (g.y2s_stride % 4 || !al16(g.y2_scale))) ||
+        (g.bias && !al16(g.bias)))
+        return fail("epilogue operands must be 16-byte aligned with channel strides that are multiples of 4");
     Tc2Geom& t = p.t;
     t.TH = g.H < 8 ? g.H : 8;
     if (!is_pow2(t.TH) || g.H % t.TH) return fail("H must be a multiple of 8 (or a power of two below 8)");
@@ -397,7 +407,7 @@ Tc2Plan plan_tc2(const ConvGeom& g) {
     if (t.cs != 1 && t.cs != 2 && t.cs != 4) t.cs = 1;
     if ((p.NT / t.cs) % 8 != 0) t.cs = 1;
     t.m_groups = (t.m_tiles + t.cs - 1) / t.cs;
-    const int fixed = 2 * t.halo_stage_bytes + STG_BYTES + 512 + 256 + 1024;
+    const int fixed = 2 * t.halo_stage_bytes + STG_BYTES + 1024 + 256 + 1024;
     int bs = (SMEM_LIMIT - fixed) / (2 * p.NT * 128);
     if (bs > MAX_BSTAGES) bs = MAX_BSTAGES;
     if (bs < 2) return fail("not enough shared memory for 2 weight stages");
