@@ -59,7 +59,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     static_assert(2 * NT + A_STAGES * 64 <= TMEM_COLS2, "TMEM budget");
 
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // keep the pointer in the shared address space (offset arithmetic on the array) so loads compile to LDS, not generic LD
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t off_b = 2 * t.halo_stage_bytes;
     const uint32_t off_stg = off_b + t.bstages * B_STAGE;
