@@ -122,6 +122,17 @@ int mn_select_text(const float* emb, const int64_t* labels, const float* s, int 
  *   wsq[c][o] = scale^2 * sum_{ky,kx} W[o][c][ky][kx]^2 (packed once at load time). */
 int mn_demod(const float* s, int s_stride, const float* wsq, float* demod, int N, int Cin, int Cout, void* stream);
 
+/* All demodulation tables of one generator pass in a single launch.  descs: DEVICE array of n_layers records;
+ * demod of layer l lands in out_all[n*out_stride + out_off .. + cout). */
+typedef struct {
+    const float* wsq;   /* [cin][cout] */
+    int32_t s_off;      /* column offset of this layer's style inside s_all rows */
+    int32_t cin, cout;
+    int32_t out_off;
+} mn_demod_desc;
+int mn_demod_batched(const float* s_all, int s_stride, const mn_demod_desc* descs, int n_layers, int max_cout,
+                     float* out_all, int out_stride, int N, void* stream);
+
 /* y = (bilinear x2 upsample, align_corners=False, of x) * s[n][c]   (up=1)
  * y = x * s[n][c]                                                   (up=0);  s may be NULL.
  * Replaces nn.Upsample / F.interpolate(scale_factor=2, mode='bilinear') at
@@ -158,9 +169,10 @@ typedef struct {
  *   out[i,:,:wv,0:C]  = (prior[i,:,y1:y1+wv,:] - mean_p)/std_p * std_l + mean_l
  *   out[i,:,:wv,C:2C] = feat[line,:,x1:x2,:]
  *   out[i,:,wv:,:]    = 0                        (wv = x2-x1, slot width = Wp)
- * std uses the unbiased variance + 1e-5.  prior:[Nc,H,Wp,C], feat:[B,H,W,C], out:[Nc,H,Wp,2C]. */
+ * std uses the unbiased variance + 1e-5.  prior:[Nc,H,Wp,C], feat:[B,H,W,C], out:[Nc,H,Wp,2C].
+ * stats_ws: >= 4*Nc*C doubles of scratch. */
 int mn_adain_concat(const float* prior, int prior_cs, const float* feat, int feat_cs, const mn_window* win,
-                    float* out, int Nc, int H, int Wp, int W, int C, void* stream);
+                    float* out, int Nc, int H, int Wp, int W, int C, double* stats_ws, void* stream);
 
 /* Write-back of the per-character modulation, models/networks.py:448-449 / :481-482:
  *   out[b,:,x,:] = feat + (feat*scale[i,:,x-x1,:] + shift[i,:,x-x1,:])  if column x of line b is

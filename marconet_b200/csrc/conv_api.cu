@@ -52,6 +52,7 @@ extern "C" int mn_conv2d_nhwc(const mn_conv_params* p, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     switch (p->precision) {
         case MN_PREC_FP32_SIMT:
+            if (mn_conv_small_supported(g)) return mn_conv_small_launch(g, st);
             g.splits = mn_conv_simt_plan_splits(g, p->workspace ? p->workspace_bytes : 0, p->split_k);
             return mn_conv_simt_launch(g, nullptr, st);
         case MN_PREC_F16X3_TC:

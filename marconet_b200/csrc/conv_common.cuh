@@ -94,3 +94,6 @@ int mn_conv_tc_launch(const ConvGeom& g, const void* w_hi, const void* w_lo, con
 // tcgen05 path v2: halo tiles + weight multicast + persistent CTAs (conv_tc2.cu)
 int mn_conv_tc2_supported(const ConvGeom& g, const char** why);
 int mn_conv_tc2_launch(const ConvGeom& g, const void* w_hi, const void* w_lo, const float* w_scale, int prec, cudaStream_t st);
+// direct 3x3 conv for Cout <= 4 (conv_small.cu)
+bool mn_conv_small_supported(const ConvGeom& g);
+int mn_conv_small_launch(const ConvGeom& g, cudaStream_t st);

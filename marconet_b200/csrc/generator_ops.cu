@@ -56,6 +56,30 @@ __global__ void demod_kernel(const float* __restrict__ s, int s_stride, const fl
     demod[(size_t)n * Cout + o] = rsqrtf(acc + 1e-8f);
 }
 
+// All demodulation tables of a generator pass in ONE launch: grid (cout tiles, N, layers), 64 columns x 4 k-slices.
+__global__ void __launch_bounds__(256) demod_batched_kernel(const float* __restrict__ s_all, int s_stride, const mn_demod_desc* __restrict__ descs,
+                                                            float* __restrict__ out_all, int out_stride) {
+    const mn_demod_desc d = descs[blockIdx.z];
+    const int col = threadIdx.x & 63, ks = threadIdx.x >> 6;
+    const int o = blockIdx.x * 64 + col;
+    const int n = blockIdx.y;
+    __shared__ float red[4][64];
+    float acc = 0.f;
+    if (o < d.cout) {
+        const float* sn = s_all + (size_t)n * s_stride + d.s_off;
+        const float* w = d.wsq + o;
+#pragma unroll 4
+        for (int c = ks; c < d.cin; c += 4) {
+            const float sv = sn[c];
+            acc = fmaf(sv * sv, w[(size_t)c * d.cout], acc);
+        }
+    }
+    red[ks][col] = acc;
+    __syncthreads();
+    if (ks == 0 && o < d.cout)
+        out_all[(size_t)n * out_stride + d.out_off + o] = rsqrtf((red[0][col] + red[1][col]) + (red[2][col] + red[3][col]) + 1e-8f);
+}
+
 // ---------------------------------------------------------------- bilinear x2 (+ per-sample channel scale)
 // PyTorch upsample_bilinear2d, align_corners=False, scale 2: src = 0.5*(dst+0.5)-0.5 clamped at 0.
 __device__ __forceinline__ void bilin_coords(int o, int size, int& i0, int& i1, float& l1) {
@@ -219,6 +243,14 @@ extern "C" int mn_torgb(const float* x, int x_cs, const float* s, int s_stride, 
         case 16: torgb_kernel<16><<<grid, 256, 0, st>>>(x, x_cs, s, s_stride, w, bias, skip, out, N, H, W, C); break;
         default: mn_set_error("mn_torgb: unsupported C=%d", C); return MN_ERR_UNSUPPORTED;
     }
+    MN_LAUNCH_CHECK();
+    return MN_OK;
+}
+
+extern "C" int mn_demod_batched(const float* s_all, int s_stride, const mn_demod_desc* descs, int n_layers, int max_cout,
+                                float* out_all, int out_stride, int N, void* stream) {
+    MN_REQUIRE(s_all && descs && out_all && n_layers > 0 && max_cout > 0 && N > 0, "mn_demod_batched: bad args");
+    demod_batched_kernel<<<dim3(mn_cdiv(max_cout, 64), N, n_layers), 256, 0, (cudaStream_t)stream>>>(s_all, s_stride, descs, out_all, out_stride);
     MN_LAUNCH_CHECK();
     return MN_OK;
 }

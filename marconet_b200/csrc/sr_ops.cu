@@ -5,37 +5,49 @@
 namespace {
 
 // ---------------------------------------------------------------- GroupNorm statistics
-// One warp = one group of 32 channels of one pixel per step; block walks a pixel chunk.
-__global__ void gn_stats_kernel(const float* __restrict__ x, int x_cs, int H, int W, int C, int cpg,
-                                const int32_t* __restrict__ valid_w, double* __restrict__ stats, int pix_per_block) {
+// Each thread owns 4 consecutive channels (float4 loads, fully coalesced rows); a block walks a pixel chunk with
+// blockDim/(C/4) pixels per iteration.  fp32 partials are flushed to fp64 every 32 pixels, reduced over the 8 lanes of a
+// 32-channel group by shuffles, over the block in shared memory, then one fp64 atomicAdd per (block, group, moment).
+__global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ x, int x_cs, int H, int W, int C, int cpg,
+                                                       const int32_t* __restrict__ valid_w, double* __restrict__ stats, int pix_per_block) {
     const int n = blockIdx.y;
-    const int G = C / cpg;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int tpp = C >> 2;                        // threads per pixel
+    const int ppi = blockDim.x / tpp;              // pixels per iteration (host guarantees >= 1)
+    const int my_c = (threadIdx.x % tpp) * 4;
+    const int my_p = threadIdx.x / tpp;
     const int wv = valid_w ? valid_w[n] : W;
     const int HW = H * W;
     const int p_begin = blockIdx.x * pix_per_block;
     const int p_end = min(HW, p_begin + pix_per_block);
-    const float* xn = x + (size_t)n * HW * x_cs;
-    // channel slots of this lane inside a group: lane, lane+32, ... (cpg is a multiple of 32 here: 32)
-    for (int g = warp; g < G; g += nwarp) {
-        float s = 0.f, ss = 0.f;
-        double ds = 0.0, dss = 0.0;
-        int cnt = 0;
-        for (int p = p_begin; p < p_end; ++p) {
-            const int px = p % W;
-            if (px >= wv) continue;
-            for (int c = lane; c < cpg; c += 32) {
-                const float v = xn[(size_t)p * x_cs + g * cpg + c];
-                s += v; ss = fmaf(v, v, ss);
-            }
-            if (++cnt == 64) { ds += (double)s; dss += (double)ss; s = 0.f; ss = 0.f; cnt = 0; }
+    const float* xn = x + (size_t)n * HW * x_cs + my_c;
+    float s = 0.f, ss = 0.f;
+    double ds = 0.0, dss = 0.0;
+    int cnt = 0;
+    if (my_p < ppi) {
+        for (int p = p_begin + my_p; p < p_end; p += ppi) {
+            if (valid_w && (p % W) >= wv) continue;
+            const float4 v = *reinterpret_cast<const float4*>(xn + (size_t)p * x_cs);
+            s += (v.x + v.y) + (v.z + v.w);
+            ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
+            if (++cnt == 32) { ds += (double)s; dss += (double)ss; s = 0.f; ss = 0.f; cnt = 0; }
         }
-        ds += (double)s; dss += (double)ss;
-        ds = mn_warp_sum_d(ds); dss = mn_warp_sum_d(dss);
-        if (lane == 0) {
-            atomicAdd(&stats[((size_t)n * G + g) * 2 + 0], ds);
-            atomicAdd(&stats[((size_t)n * G + g) * 2 + 1], dss);
-        }
+    }
+    ds += (double)s; dss += (double)ss;
+    const int lpg = cpg >> 2;                      // lanes per group (8 for 32-channel groups)
+    for (int o = lpg >> 1; o > 0; o >>= 1) {
+        ds += __shfl_xor_sync(0xffffffffu, ds, o);
+        dss += __shfl_xor_sync(0xffffffffu, dss, o);
+    }
+    __shared__ double red[2][64];                  // [moment][group-slot]: blockDim/lpg <= 32 slots used
+    const int slot = threadIdx.x / lpg;            // (pixel slot, group) pair index
+    if ((threadIdx.x % lpg) == 0) { red[0][slot] = ds; red[1][slot] = dss; }
+    __syncthreads();
+    const int G = C / cpg;
+    if (threadIdx.x < G) {
+        double a = 0.0, b2 = 0.0;
+        for (int k = 0; k < ppi; ++k) { a += red[0][k * G + threadIdx.x]; b2 += red[1][k * G + threadIdx.x]; }
+        atomicAdd(&stats[((size_t)n * G + threadIdx.x) * 2 + 0], a);
+        atomicAdd(&stats[((size_t)n * G + threadIdx.x) * 2 + 1], b2);
     }
 }
 
@@ -75,71 +87,96 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, int x_cs, float* __
 }
 
 // ---------------------------------------------------------------- AdaIN + concat
-// grid (Nc, C/32), 256 threads: lane = channel inside the 32-chunk, 8 warps stride over window pixels.
-__global__ void adain_concat_kernel(const float* __restrict__ prior, int prior_cs, const float* __restrict__ feat, int feat_cs,
-                                    const mn_window* __restrict__ win, float* __restrict__ out,
-                                    int H, int Wp, int W, int C) {
-    const int i = blockIdx.x;
-    const int c = blockIdx.y * 32 + (threadIdx.x & 31);
-    const int warp = threadIdx.x >> 5;
+// Pass 1: per (character, channel) sum / sum-of-squares of the prior crop and of the LR-feature window, fp64 atomics.
+// Pass 2: elementwise normalise + concat.  Both passes use float4 channel vectors (coalesced pixel rows).
+__global__ void __launch_bounds__(256) adain_stats_kernel(const float* __restrict__ prior, int prior_cs, const float* __restrict__ feat, int feat_cs,
+                                                          const mn_window* __restrict__ win, double* __restrict__ stats,
+                                                          int H, int Wp, int W, int C, int pix_per_block) {
+    const int i = blockIdx.y;
     const mn_window wn = win[i];
     const int wv = wn.x2 - wn.x1;
     const int npix = H * wv;
-    const float* pr = prior + (size_t)i * H * Wp * prior_cs + c;
-    const float* ft = feat + (size_t)wn.line * H * W * feat_cs + c;
-    float* op = out + (size_t)i * H * Wp * (2 * C);
-    __shared__ float red[4][8][32];
-    __shared__ float st[4][32];   // pm, ps, lm, ls
+    const int tpp = C >> 2, ppi = blockDim.x / tpp;
+    const int my_c = (threadIdx.x % tpp) * 4, my_p = threadIdx.x / tpp;
+    const int p_begin = blockIdx.x * pix_per_block, p_end = min(npix, p_begin + pix_per_block);
+    const float* pr = prior + (size_t)i * H * Wp * prior_cs + my_c;
+    const float* ft = feat + (size_t)wn.line * H * W * feat_cs + my_c;
+    float4 sp = make_float4(0.f, 0.f, 0.f, 0.f), qp = sp, sl = sp, ql = sp;
+    double acc[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc[k] = 0.0;
+    int cnt = 0;
+    auto flush = [&]() {
+        acc[0] += sp.x; acc[1] += sp.y; acc[2] += sp.z; acc[3] += sp.w; acc[4] += qp.x; acc[5] += qp.y; acc[6] += qp.z; acc[7] += qp.w;
+        acc[8] += sl.x; acc[9] += sl.y; acc[10] += sl.z; acc[11] += sl.w; acc[12] += ql.x; acc[13] += ql.y; acc[14] += ql.z; acc[15] += ql.w;
+        sp = qp = sl = ql = make_float4(0.f, 0.f, 0.f, 0.f);
+        cnt = 0;
+    };
+    if (my_p < ppi && wv > 0) {
+        for (int p = p_begin + my_p; p < p_end; p += ppi) {
+            const int yy = p / wv, xx = p - yy * wv;
+            const float4 a = *reinterpret_cast<const float4*>(pr + ((size_t)yy * Wp + wn.y1 + xx) * prior_cs);
+            const float4 b = *reinterpret_cast<const float4*>(ft + ((size_t)yy * W + wn.x1 + xx) * feat_cs);
+            sp.x += a.x; sp.y += a.y; sp.z += a.z; sp.w += a.w;
+            qp.x = fmaf(a.x, a.x, qp.x); qp.y = fmaf(a.y, a.y, qp.y); qp.z = fmaf(a.z, a.z, qp.z); qp.w = fmaf(a.w, a.w, qp.w);
+            sl.x += b.x; sl.y += b.y; sl.z += b.z; sl.w += b.w;
+            ql.x = fmaf(b.x, b.x, ql.x); ql.y = fmaf(b.y, b.y, ql.y); ql.z = fmaf(b.z, b.z, ql.z); ql.w = fmaf(b.w, b.w, ql.w);
+            if (++cnt == 16) flush();
+        }
+    }
+    flush();
+    // reduce the ppi pixel slots of the block in shared memory, then one atomic per (block, channel, moment)
+    __shared__ double red[256][17];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) red[threadIdx.x][k] = acc[k];
+    __syncthreads();
+    if (my_p == 0) {
+        for (int sl2 = 1; sl2 < ppi; ++sl2)
+#pragma unroll
+            for (int k = 0; k < 16; ++k) acc[k] += red[sl2 * tpp + threadIdx.x][k];
+        double* st = stats + ((size_t)i * C + my_c) * 4;          // [i][c][{sum_p, sq_p, sum_l, sq_l}]
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            atomicAdd(st + j * 4 + 0, acc[j]); atomicAdd(st + j * 4 + 1, acc[4 + j]);
+            atomicAdd(st + j * 4 + 2, acc[8 + j]); atomicAdd(st + j * 4 + 3, acc[12 + j]);
+        }
+    }
+}
 
-    if (wv > 0) {
-        float sp = 0.f, sl = 0.f;
-        for (int p = warp; p < npix; p += 8) {
-            const int yy = p / wv, xx = p - yy * wv;
-            sp += pr[((size_t)yy * Wp + wn.y1 + xx) * prior_cs];
-            sl += ft[((size_t)yy * W + wn.x1 + xx) * feat_cs];
+__global__ void adain_apply_kernel(const float* __restrict__ prior, int prior_cs, const float* __restrict__ feat, int feat_cs,
+                                   const mn_window* __restrict__ win, const double* __restrict__ stats, float* __restrict__ out,
+                                   int Nc, int H, int Wp, int W, int C) {
+    const int c4 = C >> 2;
+    const int64_t total = (int64_t)Nc * H * Wp * c4;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c = (int)(idx % c4) * 4;
+    int64_t pix = idx / c4;
+    const int xx = (int)(pix % Wp);
+    const int yy = (int)((pix / Wp) % H);
+    const int i = (int)(pix / ((int64_t)Wp * H));
+    const mn_window wn = win[i];
+    const int wv = wn.x2 - wn.x1;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (xx < wv) {
+        const float4 pv = *reinterpret_cast<const float4*>(prior + (((size_t)i * H + yy) * Wp + wn.y1 + xx) * prior_cs + c);
+        b = *reinterpret_cast<const float4*>(feat + (((size_t)wn.line * H + yy) * W + wn.x1 + xx) * feat_cs + c);
+        const double cnt = (double)H * wv;
+        float pvv[4] = {pv.x, pv.y, pv.z, pv.w}, o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double* st = stats + ((size_t)i * C + c + j) * 4;
+            const double pm = st[0] / cnt, lm = st[2] / cnt;
+            double pvar = (st[1] - st[0] * pm) / (cnt - 1.0), lvar = (st[3] - st[2] * lm) / (cnt - 1.0);   // unbiased (torch.var default)
+            pvar = pvar < 0.0 ? 0.0 : pvar; lvar = lvar < 0.0 ? 0.0 : lvar;
+            const float ps = sqrtf((float)pvar + 1e-5f), ls = sqrtf((float)lvar + 1e-5f);
+            o[j] = __fadd_rn(__fmul_rn(__fdiv_rn(pvv[j] - (float)pm, ps), ls), (float)lm);
         }
-        red[0][warp][threadIdx.x & 31] = sp;
-        red[1][warp][threadIdx.x & 31] = sl;
-        __syncthreads();
-        if (warp == 0) {
-            float a = 0.f, b = 0.f;
-            for (int k = 0; k < 8; ++k) { a += red[0][k][threadIdx.x]; b += red[1][k][threadIdx.x]; }
-            st[0][threadIdx.x] = a / (float)npix;
-            st[2][threadIdx.x] = b / (float)npix;
-        }
-        __syncthreads();
-        const float pm = st[0][threadIdx.x & 31], lm = st[2][threadIdx.x & 31];
-        float vp = 0.f, vl = 0.f;
-        for (int p = warp; p < npix; p += 8) {
-            const int yy = p / wv, xx = p - yy * wv;
-            const float a = pr[((size_t)yy * Wp + wn.y1 + xx) * prior_cs] - pm;
-            const float b = ft[((size_t)yy * W + wn.x1 + xx) * feat_cs] - lm;
-            vp = fmaf(a, a, vp); vl = fmaf(b, b, vl);
-        }
-        red[2][warp][threadIdx.x & 31] = vp;
-        red[3][warp][threadIdx.x & 31] = vl;
-        __syncthreads();
-        if (warp == 0) {
-            float a = 0.f, b = 0.f;
-            for (int k = 0; k < 8; ++k) { a += red[2][k][threadIdx.x]; b += red[3][k][threadIdx.x]; }
-            st[1][threadIdx.x] = sqrtf(a / (float)(npix - 1) + 1e-5f);
-            st[3][threadIdx.x] = sqrtf(b / (float)(npix - 1) + 1e-5f);
-        }
-        __syncthreads();
+        a = make_float4(o[0], o[1], o[2], o[3]);
     }
-    const float pm = st[0][threadIdx.x & 31], ps = st[1][threadIdx.x & 31];
-    const float lm = st[2][threadIdx.x & 31], ls = st[3][threadIdx.x & 31];
-    for (int p = warp; p < H * Wp; p += 8) {
-        const int yy = p / Wp, xx = p - yy * Wp;
-        float a = 0.f, b = 0.f;
-        if (xx < wv) {
-            const float pv = pr[((size_t)yy * Wp + wn.y1 + xx) * prior_cs];
-            b = ft[((size_t)yy * W + wn.x1 + xx) * feat_cs];
-            a = __fadd_rn(__fmul_rn(__fdiv_rn(pv - pm, ps), ls), lm);
-        }
-        op[(size_t)p * (2 * C) + c] = a;
-        op[(size_t)p * (2 * C) + C + c] = b;
-    }
+    float* op = out + pix * (2 * C);
+    *reinterpret_cast<float4*>(op + c) = a;
+    *reinterpret_cast<float4*>(op + C + c) = b;
 }
 
 // ---------------------------------------------------------------- window write-back
@@ -185,8 +222,9 @@ extern "C" int mn_groupnorm_swish(const float* x, int x_cs, float* y, int y_cs, 
     const int G = C / cpg;
     MN_CUDA_CHECK(cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * N * G, st));
     const int HW = H * W;
-    int blocks = mn_cdiv(mn_num_sms() * 4, N);
-    if (blocks > mn_cdiv(HW, 16)) blocks = mn_cdiv(HW, 16);
+    MN_REQUIRE(cpg == 32 && (256 % (C >> 2)) == 0 && C <= 1024, "mn_groupnorm_swish: needs 32 channels per group and C/4 dividing 256");
+    int blocks = mn_cdiv(mn_num_sms() * 8, N);
+    if (blocks > mn_cdiv(HW, 64)) blocks = mn_cdiv(HW, 64);
     if (blocks < 1) blocks = 1;
     const int ppb = mn_cdiv(HW, blocks);
     blocks = mn_cdiv(HW, ppb);
@@ -199,9 +237,23 @@ extern "C" int mn_groupnorm_swish(const float* x, int x_cs, float* y, int y_cs, 
 }
 
 extern "C" int mn_adain_concat(const float* prior, int prior_cs, const float* feat, int feat_cs, const mn_window* win,
-                               float* out, int Nc, int H, int Wp, int W, int C, void* stream) {
-    MN_REQUIRE(prior && feat && win && out && Nc > 0 && H > 0 && Wp > 0 && W > 0 && C > 0 && C % 32 == 0, "mn_adain_concat: bad args");
-    adain_concat_kernel<<<dim3(Nc, C / 32), 256, 0, (cudaStream_t)stream>>>(prior, prior_cs, feat, feat_cs, win, out, H, Wp, W, C);
+                               float* out, int Nc, int H, int Wp, int W, int C, double* stats_ws, void* stream) {
+    MN_REQUIRE(prior && feat && win && out && stats_ws && Nc > 0 && H > 0 && Wp > 0 && W > 0 && C > 0, "mn_adain_concat: bad args");
+    MN_REQUIRE((C & 3) == 0 && 256 % (C >> 2) == 0 && (prior_cs & 3) == 0 && (feat_cs & 3) == 0 &&
+               ((uintptr_t)prior & 15) == 0 && ((uintptr_t)feat & 15) == 0 && ((uintptr_t)out & 15) == 0,
+               "mn_adain_concat: C/4 must divide 256 and all operands must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    MN_CUDA_CHECK(cudaMemsetAsync(stats_ws, 0, sizeof(double) * 4 * (size_t)Nc * C, st));
+    const int npix_max = H * Wp;
+    int blocks = mn_cdiv(mn_num_sms() * 4, Nc);
+    if (blocks > mn_cdiv(npix_max, 32)) blocks = mn_cdiv(npix_max, 32);
+    if (blocks < 1) blocks = 1;
+    const int ppb = mn_cdiv(npix_max, blocks);
+    blocks = mn_cdiv(npix_max, ppb);
+    adain_stats_kernel<<<dim3(blocks, Nc), 256, 0, st>>>(prior, prior_cs, feat, feat_cs, win, stats_ws, H, Wp, W, C, ppb);
+    MN_LAUNCH_CHECK();
+    const int64_t total = (int64_t)Nc * H * Wp * (C >> 2);
+    adain_apply_kernel<<<(unsigned)mn_cdiv64(total, 256), 256, 0, st>>>(prior, prior_cs, feat, feat_cs, win, stats_ws, out, Nc, H, Wp, W, C);
     MN_LAUNCH_CHECK();
     return MN_OK;
 }

@@ -227,6 +227,13 @@ class TextGenerator(_PackedModule):
             w = (m.conv.weight[0, :, :, 0, 0] * m.conv.scale).contiguous()          # [3, Cin]
             pk["rgb"].append(dict(w=w, bias=m.bias.reshape(-1).contiguous(), off=offs[len(styled) + i]))
         pk["emb"] = self.input_text.TextEmbeddings[:, :, 0, 0].contiguous()
+        entries, off = [], 0
+        for e in pk["styled"]:
+            entries.append((e["wsq"], e["off"][0], off))
+            e["demod_off"] = off
+            off += e["cout"]
+        pk["demod_table"] = ops.make_demod_table(entries, device)
+        pk["demod_total"] = off
         return pk
 
     # ---- forward --------------------------------------------------------------------------
@@ -257,7 +264,8 @@ class TextGenerator(_PackedModule):
             return s_all[:, o:o + c]
 
         st = pk["styled"]
-        demods = [ops.demod(s_of(e), e["wsq"]) for e in st]
+        demod_all = ops.demod_batched(s_all, pk["demod_table"], pk["demod_total"])       # [N, sum Cout], one launch
+        demods = [demod_all[:, e["demod_off"]:e["demod_off"] + e["cout"]] for e in st]
 
         def styled(i, x, want_y, next_i=None):
             e = st[i]

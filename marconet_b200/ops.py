@@ -212,6 +212,30 @@ def demod(s, wsq):
     return out
 
 
+def make_demod_table(entries, device):
+    """entries: [(wsq tensor [cin,cout], s_off, out_off)] -> (device byte tensor holding mn_demod_desc[], n, max_cout, total_out)."""
+    import numpy as np
+    arr = (_lib.DemodDesc * len(entries))()
+    mx = 0
+    for i, (wsq, s_off, out_off) in enumerate(entries):
+        arr[i].wsq = wsq.data_ptr(); arr[i].s_off = s_off; arr[i].cin = wsq.shape[0]; arr[i].cout = wsq.shape[1]; arr[i].out_off = out_off
+        mx = max(mx, wsq.shape[1])
+    raw = torch.from_numpy(np.frombuffer(bytes(arr), dtype=np.uint8).copy()).to(device)
+    return raw, len(entries), mx
+
+
+def demod_batched(s_all, table, out_total):
+    """One launch for every styled conv's demodulation vector; returns [N, out_total]."""
+    global LAUNCHES
+    raw, n_layers, mx = table
+    n = s_all.shape[0]
+    out = torch.empty((n, out_total), dtype=torch.float32, device=s_all.device)
+    _lib.check(_lib.load().mn_demod_batched(_ptr(s_all), s_all.stride(0), _ptr(raw), n_layers, mx, _ptr(out), out_total, n, _stream()),
+               "mn_demod_batched")
+    LAUNCHES += 1
+    return out
+
+
 def resample_modulate(x, s=None, up=False, out=None):
     global LAUNCHES
     n, h, w, c, x_cs = nhwc_info(x, "x")
@@ -254,9 +278,10 @@ def adain_concat(prior, feat, win_dev, nc, wp):
     if pn != nc or pw != wp or fh != h or fc != c:
         raise RuntimeError("adain_concat: shape mismatch")
     out = torch.empty((nc, h, wp, 2 * c), dtype=torch.float32, device=feat.device)
+    stats = torch.empty((nc * c * 4,), dtype=torch.float64, device=feat.device)
     _lib.check(_lib.load().mn_adain_concat(_ptr(prior), p_cs, _ptr(feat), f_cs, _ptr(win_dev), _ptr(out), nc, h, wp, w, c,
-                                           _stream()), "mn_adain_concat")
-    LAUNCHES += 1
+                                           _ptr(stats), _stream()), "mn_adain_concat")
+    LAUNCHES += 3
     return out
 
 

@@ -62,6 +62,18 @@ def test_conv_plain(case):
     _close(_nchw(y), ref, 2e-5, f"conv {case}")
 
 
+@pytest.mark.parametrize("shape", [(2, 13, 45, 64, 3), (1, 16, 64, 32, 1), (1, 128, 256, 64, 3)])
+def test_conv_small_cout_direct_kernel(shape):
+    from marconet_b200 import ops
+    n, h, w, cin, cout = shape
+    x = _rand(n, cin, h, w, seed=60)
+    wt = _rand(cout, cin, 3, 3, seed=61, scale=0.05)
+    bias = _rand(cout, seed=62)
+    ref = torch.tanh(F.conv2d(x, wt, bias, padding=1))
+    y = ops.conv2d(_nhwc(x), _pack(wt), 3, 3, pad=(1, 1), bias=bias.to(_dev()), act=ops.ACT_TANH, precision=ops.PREC_FP32_SIMT)
+    _close(_nchw(y), ref, 1e-5, f"small-cout conv {shape}")
+
+
 def test_conv_forced_splitk_matches():
     from marconet_b200 import ops
     x = _rand(2, 256, 8, 8, seed=3)
