@@ -152,7 +152,7 @@ int mn_torgb(const float* x, int x_cs, const float* s, int s_stride, const float
  * ------------------------------------------------------------------------------------ */
 /* GroupNorm(32 channels/group, eps) + optional swish, models/networks.py:487-493,508-512.
  * Statistics run over H x valid_w[n] pixels per sample (valid_w NULL -> W); columns beyond
- * valid_w[n] are written as 0.  stats_ws: >= N*(C/cpg)*2 doubles. */
+ * valid_w[n] are written as 0.  stats_ws: >= N*(C/cpg)*3 doubles of scratch. */
 int mn_groupnorm_swish(const float* x, int x_cs, float* y, int y_cs, const float* gamma, const float* beta,
                        int N, int H, int W, int C, int cpg, float eps, int swish,
                        const int32_t* valid_w, double* stats_ws, void* stream);
@@ -170,7 +170,7 @@ typedef struct {
  *   out[i,:,:wv,C:2C] = feat[line,:,x1:x2,:]
  *   out[i,:,wv:,:]    = 0                        (wv = x2-x1, slot width = Wp)
  * std uses the unbiased variance + 1e-5.  prior:[Nc,H,Wp,C], feat:[B,H,W,C], out:[Nc,H,Wp,2C].
- * stats_ws: >= 4*Nc*C doubles of scratch. */
+ * stats_ws: >= 6*Nc*C doubles of scratch. */
 int mn_adain_concat(const float* prior, int prior_cs, const float* feat, int feat_cs, const mn_window* win,
                     float* out, int Nc, int H, int Wp, int W, int C, double* stats_ws, void* stream);
 
@@ -188,6 +188,12 @@ int mn_window_scatter(const float* feat, int feat_cs, const float* scale, const 
 /* nn.LayerNorm over the last dim (eps 1e-5), models/textvit_arch.py:41,46,53,58,85,99. */
 int mn_layernorm(const float* x, float* y, const float* gamma, const float* beta, int rows, int dim,
                  float eps, void* stream);
+
+/* nn.Linear for M <= 64 rows (the tokens of one text line), models/textvit_arch.py:42,46-51,57,61,86-88,101-102:
+ *   y[M][N] = act(x[M][K] w[K][N] + bias[N] + residual[M][N]) * gain, K % 32 == 0, N % 16 == 0.  (Note: residual is added
+ *   BEFORE the activation, like mn_conv2d_nhwc.) */
+int mn_linear_small_m(const float* x, const float* w, const float* bias, const float* residual, float* y,
+                      int M, int K, int N, int act, float gain, void* stream);
 
 /* LayerNorm over the TOKEN axis followed by Linear(T -> To) over the token axis, i.e. the
  * `x.permute(0,2,1)` -> LayerNorm(T) -> Linear -> permute(0,2,1) idiom at

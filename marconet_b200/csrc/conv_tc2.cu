@@ -400,7 +400,9 @@ Tc2Plan plan_tc2(const ConvGeom& g) {
     t.tiles_w = g.W / t.TW; t.tiles_h = g.H / t.TH; t.tiles_n = (g.N + t.TN - 1) / t.TN;
     t.m_tiles = t.tiles_w * t.tiles_h * t.tiles_n;
     t.cblocks = g.Cin / KB; t.taps = g.KH * g.KW;
-    p.NT = (g.Cout % 128 == 0) ? 128 : 64;
+    // 128-wide channel tiles unless that leaves most SMs idle (small-M layers at batch 1: ResNet 8x512 maps, 8x8 / 16x16
+    // generator layers): then 64-wide tiles double the number of work items.
+    p.NT = (g.Cout % 128 == 0 && (int64_t)((t.m_tiles + 1) / 2) * (g.Cout / 128) * 2 >= 120) ? 128 : 64;
     t.n_tiles = g.Cout / p.NT;
     static int force_cs = -1;
     if (force_cs < 0) { const char* e = getenv("MN_TC_CLUSTER"); force_cs = e ? atoi(e) : 0; }

@@ -51,10 +51,24 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
     }
 }
 
+// (sum, sumsq) fp64 -> (mean, rstd) fp32 per (sample, group); biased variance like torch.nn.GroupNorm.
+__global__ void gn_finalize_kernel(const double* __restrict__ stats, float2* __restrict__ mr, int N, int G, int H, int W, int cpg, float eps,
+                                   const int32_t* __restrict__ valid_w) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * G) return;
+    const int n = i / G;
+    const int wv = valid_w ? valid_w[n] : W;
+    const double cnt = (double)H * wv * cpg;
+    const double mean = cnt > 0 ? stats[2 * i] / cnt : 0.0;
+    double var = cnt > 0 ? stats[2 * i + 1] / cnt - mean * mean : 0.0;
+    if (var < 0.0) var = 0.0;
+    mr[i] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+}
+
 __global__ void gn_apply_kernel(const float* __restrict__ x, int x_cs, float* __restrict__ y, int y_cs,
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 int N, int H, int W, int C, int cpg, float eps, int swish,
-                                const int32_t* __restrict__ valid_w, const double* __restrict__ stats) {
+                                const int32_t* __restrict__ valid_w, const float2* __restrict__ mr) {
     const int c4 = C >> 2;
     const int64_t total = (int64_t)N * H * W * c4;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -67,17 +81,15 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, int x_cs, float* __
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
     if (px < wv) {
         const int G = C / cpg, g = c / cpg;
-        const double cnt = (double)H * wv * cpg;
-        const double mean_d = stats[((size_t)n * G + g) * 2] / cnt;
-        double var_d = stats[((size_t)n * G + g) * 2 + 1] / cnt - mean_d * mean_d;
-        if (var_d < 0.0) var_d = 0.0;
-        const float mean = (float)mean_d;
-        const float rstd = (float)(1.0 / sqrt(var_d + (double)eps));
+        const float2 m2 = mr[(size_t)n * G + g];
+        const float mean = m2.x, rstd = m2.y;
         const float4 v = *reinterpret_cast<const float4*>(x + pix * x_cs + c);
+        const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
+        const float gam[4] = {ga.x, ga.y, ga.z, ga.w}, bet[4] = {be.x, be.y, be.z, be.w};
         float t[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            float u = (t[j] - mean) * rstd * gamma[c + j] + beta[c + j];
+            float u = (t[j] - mean) * rstd * gam[j] + bet[j];
             if (swish) u = u * (1.f / (1.f + expf(-u)));
             t[j] = u;
         }
@@ -143,8 +155,22 @@ __global__ void __launch_bounds__(256) adain_stats_kernel(const float* __restric
     }
 }
 
+// fp64 moments -> fp32 {prior mean, prior std, lq mean, lq std} per (character, channel); unbiased variance + 1e-5.
+__global__ void adain_finalize_kernel(const double* __restrict__ stats, const mn_window* __restrict__ win, float4* __restrict__ ms,
+                                      int Nc, int C, int H) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= Nc * C) return;
+    const mn_window wn = win[idx / C];
+    const double cnt = (double)H * (wn.x2 - wn.x1);
+    const double* st = stats + (size_t)idx * 4;
+    const double pm = st[0] / cnt, lm = st[2] / cnt;
+    double pvar = (st[1] - st[0] * pm) / (cnt - 1.0), lvar = (st[3] - st[2] * lm) / (cnt - 1.0);
+    pvar = pvar < 0.0 ? 0.0 : pvar; lvar = lvar < 0.0 ? 0.0 : lvar;
+    ms[idx] = make_float4((float)pm, sqrtf((float)pvar + 1e-5f), (float)lm, sqrtf((float)lvar + 1e-5f));
+}
+
 __global__ void adain_apply_kernel(const float* __restrict__ prior, int prior_cs, const float* __restrict__ feat, int feat_cs,
-                                   const mn_window* __restrict__ win, const double* __restrict__ stats, float* __restrict__ out,
+                                   const mn_window* __restrict__ win, const float4* __restrict__ ms, float* __restrict__ out,
                                    int Nc, int H, int Wp, int W, int C) {
     const int c4 = C >> 2;
     const int64_t total = (int64_t)Nc * H * Wp * c4;
@@ -161,16 +187,11 @@ __global__ void adain_apply_kernel(const float* __restrict__ prior, int prior_cs
     if (xx < wv) {
         const float4 pv = *reinterpret_cast<const float4*>(prior + (((size_t)i * H + yy) * Wp + wn.y1 + xx) * prior_cs + c);
         b = *reinterpret_cast<const float4*>(feat + (((size_t)wn.line * H + yy) * W + wn.x1 + xx) * feat_cs + c);
-        const double cnt = (double)H * wv;
         float pvv[4] = {pv.x, pv.y, pv.z, pv.w}, o[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const double* st = stats + ((size_t)i * C + c + j) * 4;
-            const double pm = st[0] / cnt, lm = st[2] / cnt;
-            double pvar = (st[1] - st[0] * pm) / (cnt - 1.0), lvar = (st[3] - st[2] * lm) / (cnt - 1.0);   // unbiased (torch.var default)
-            pvar = pvar < 0.0 ? 0.0 : pvar; lvar = lvar < 0.0 ? 0.0 : lvar;
-            const float ps = sqrtf((float)pvar + 1e-5f), ls = sqrtf((float)lvar + 1e-5f);
-            o[j] = __fadd_rn(__fmul_rn(__fdiv_rn(pvv[j] - (float)pm, ps), ls), (float)lm);
+            const float4 q = ms[(size_t)i * C + c + j];          // {prior mean, prior std, lq mean, lq std}
+            o[j] = __fadd_rn(__fmul_rn(__fdiv_rn(pvv[j] - q.x, q.y), q.w), q.z);
         }
         a = make_float4(o[0], o[1], o[2], o[3]);
     }
@@ -230,8 +251,11 @@ extern "C" int mn_groupnorm_swish(const float* x, int x_cs, float* y, int y_cs, 
     blocks = mn_cdiv(HW, ppb);
     gn_stats_kernel<<<dim3(blocks, N), 256, 0, st>>>(x, x_cs, H, W, C, cpg, valid_w, stats_ws, ppb);
     MN_LAUNCH_CHECK();
+    float2* mr = reinterpret_cast<float2*>(stats_ws + 2 * (size_t)N * G);      // second half of the workspace
+    gn_finalize_kernel<<<mn_cdiv(N * G, 128), 128, 0, st>>>(stats_ws, mr, N, G, H, W, cpg, eps, valid_w);
+    MN_LAUNCH_CHECK();
     const int64_t total = (int64_t)N * H * W * (C >> 2);
-    gn_apply_kernel<<<(unsigned)mn_cdiv64(total, 256), 256, 0, st>>>(x, x_cs, y, y_cs, gamma, beta, N, H, W, C, cpg, eps, swish, valid_w, stats_ws);
+    gn_apply_kernel<<<(unsigned)mn_cdiv64(total, 256), 256, 0, st>>>(x, x_cs, y, y_cs, gamma, beta, N, H, W, C, cpg, eps, swish, valid_w, mr);
     MN_LAUNCH_CHECK();
     return MN_OK;
 }
@@ -252,8 +276,11 @@ extern "C" int mn_adain_concat(const float* prior, int prior_cs, const float* fe
     blocks = mn_cdiv(npix_max, ppb);
     adain_stats_kernel<<<dim3(blocks, Nc), 256, 0, st>>>(prior, prior_cs, feat, feat_cs, win, stats_ws, H, Wp, W, C, ppb);
     MN_LAUNCH_CHECK();
+    float4* ms = reinterpret_cast<float4*>(stats_ws + 4 * (size_t)Nc * C);    // second part of the workspace
+    adain_finalize_kernel<<<mn_cdiv(Nc * C, 256), 256, 0, st>>>(stats_ws, win, ms, Nc, C, H);
+    MN_LAUNCH_CHECK();
     const int64_t total = (int64_t)Nc * H * Wp * (C >> 2);
-    adain_apply_kernel<<<(unsigned)mn_cdiv64(total, 256), 256, 0, st>>>(prior, prior_cs, feat, feat_cs, win, stats_ws, out, Nc, H, Wp, W, C);
+    adain_apply_kernel<<<(unsigned)mn_cdiv64(total, 256), 256, 0, st>>>(prior, prior_cs, feat, feat_cs, win, ms, out, Nc, H, Wp, W, C);
     MN_LAUNCH_CHECK();
     return MN_OK;
 }

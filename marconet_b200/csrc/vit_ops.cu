@@ -92,6 +92,71 @@ __global__ void __launch_bounds__(256) attention_kernel(const float* __restrict_
     }
 }
 
+// Small-M linear layer (M <= 64 rows: the 64 / 16 tokens of one text line): y = act(x W + b) * gain + residual.
+// One block = all M rows x 16 output columns, K streamed in 32-wide chunks with register-prefetched double buffering.
+// No split-K, no second pass: the TextViT's ~45 GEMMs per line are launch/latency bound, not FLOP bound.
+__global__ void __launch_bounds__(128) linear_small_m_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, const float* __restrict__ residual,
+                                                             float* __restrict__ y, int M, int K, int N, int act, float gain) {
+    __shared__ __align__(16) float Xs[2][64][36];
+    __shared__ __align__(16) float Ws[2][32][16];
+    const int tid = threadIdx.x;
+    const int col = tid & 15, rg = tid >> 4;            // 16 columns x 8 row groups of 8 rows
+    const int n0 = blockIdx.x * 16;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    float4 xr[4], wr;
+    auto gload = [&](int k0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {                   // X chunk: 64 rows x 32 floats = 512 float4
+            const int idx = tid + i * 128, r = idx >> 3, c4 = (idx & 7) * 4;
+            xr[i] = r < M ? __ldg(reinterpret_cast<const float4*>(x + (size_t)r * K + k0 + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const int kr = tid >> 2, c4 = (tid & 3) * 4;    // W chunk: 32 rows x 16 floats = 128 float4
+        wr = __ldg(reinterpret_cast<const float4*>(w + (size_t)(k0 + kr) * N + n0 + c4));
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int idx = tid + i * 128, r = idx >> 3, c4 = (idx & 7) * 4;
+            *reinterpret_cast<float4*>(&Xs[buf][r][c4]) = xr[i];
+        }
+        *reinterpret_cast<float4*>(&Ws[buf][tid >> 2][(tid & 3) * 4]) = wr;
+    };
+    const int nchunks = K / 32;
+    gload(0);
+    sstore(0);
+    __syncthreads();
+    for (int ch = 0; ch < nchunks; ++ch) {
+        const int buf = ch & 1;
+        if (ch + 1 < nchunks) gload((ch + 1) * 32);
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4) {
+            const float w0 = Ws[buf][k4 * 4][col], w1 = Ws[buf][k4 * 4 + 1][col], w2 = Ws[buf][k4 * 4 + 2][col], w3 = Ws[buf][k4 * 4 + 3][col];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 xv = *reinterpret_cast<const float4*>(&Xs[buf][rg * 8 + i][k4 * 4]);
+                acc[i] = fmaf(xv.x, w0, acc[i]); acc[i] = fmaf(xv.y, w1, acc[i]);
+                acc[i] = fmaf(xv.z, w2, acc[i]); acc[i] = fmaf(xv.w, w3, acc[i]);
+            }
+        }
+        if (ch + 1 < nchunks) sstore(buf ^ 1);
+        __syncthreads();
+    }
+    const int o = n0 + col;
+    const float b = bias ? bias[o] : 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = rg * 8 + i;
+        if (r < M) {
+            float v = acc[i] + b;
+            if (residual) v += residual[(size_t)r * N + o];
+            y[(size_t)r * N + o] = mn_apply_act(v, act) * gain;
+        }
+    }
+}
+
 // 32x32 smem-tiled transposes between [C][HW] and [HW][C] per sample.
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int HW, int y_cs) {
     __shared__ float t[32][33];
@@ -128,6 +193,15 @@ extern "C" int mn_layernorm(const float* x, float* y, const float* gamma, const 
                             float eps, void* stream) {
     MN_REQUIRE(x && y && gamma && beta && rows > 0 && dim > 0, "mn_layernorm: bad args");
     layernorm_kernel<<<mn_cdiv(rows, 4), 128, 0, (cudaStream_t)stream>>>(x, y, gamma, beta, rows, dim, eps);
+    MN_LAUNCH_CHECK();
+    return MN_OK;
+}
+
+extern "C" int mn_linear_small_m(const float* x, const float* w, const float* bias, const float* residual, float* y,
+                                 int M, int K, int N, int act, float gain, void* stream) {
+    MN_REQUIRE(x && w && y && M > 0 && M <= 64 && K > 0 && K % 32 == 0 && N > 0 && N % 16 == 0, "mn_linear_small_m: needs M<=64, K%32==0, N%16==0");
+    MN_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0, "mn_linear_small_m: x, w must be 16-byte aligned");
+    linear_small_m_kernel<<<N / 16, 128, 0, (cudaStream_t)stream>>>(x, w, bias, residual, y, M, K, N, act, gain);
     MN_LAUNCH_CHECK();
     return MN_OK;
 }

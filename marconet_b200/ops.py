@@ -103,7 +103,7 @@ class ConvWeight:
         return got
 
 
-TC_MIN_FLOP = 2.0e8    # below this a launch is latency-bound either way; stay on the exact fp32 path
+TC_MIN_FLOP = 3.0e7    # tiny launches are latency-bound either way and stay on the exact fp32 path
 
 
 def conv2d(x, w, kh, kw, stride=(1, 1), pad=(0, 0), bias=None, out_scale=None, residual=None,
@@ -174,7 +174,17 @@ def conv2d(x, w, kh, kw, stride=(1, 1), pad=(0, 0), bias=None, out_scale=None, r
 
 def linear(x2d, w, bias=None, act=ACT_NONE, gain=1.0, residual=None, out=None, precision=None):
     """nn.Linear as a 1x1 conv on [M,1,1,K]; ``w`` packed [K, Cout]; x2d: [M, K] contiguous."""
+    global LAUNCHES
     m, k = x2d.shape
+    wt = w.w if isinstance(w, ConvWeight) else w
+    nout = wt.shape[1]
+    if m <= 64 and k % 32 == 0 and nout % 16 == 0 and precision is None and x2d.is_contiguous() and \
+            (residual is None or residual.is_contiguous()):
+        y = out if out is not None else torch.empty((m, nout), dtype=torch.float32, device=x2d.device)
+        _lib.check(_lib.load().mn_linear_small_m(_ptr(x2d), _ptr(wt), _ptr(bias), _ptr(residual), _ptr(y), m, k, nout, act, gain,
+                                                 _stream()), "mn_linear_small_m")
+        LAUNCHES += 1
+        return y
     res = None if residual is None else residual.reshape(m, 1, 1, -1)
     o = None if out is None else out.reshape(m, 1, 1, -1)
     y = conv2d(x2d.reshape(m, 1, 1, k), w, 1, 1, bias=bias, act=act, gain=gain, residual=res, out=o, precision=precision)
@@ -263,7 +273,7 @@ def groupnorm_swish(x, gamma, beta, cpg=32, eps=1e-6, swish=True, valid_w=None, 
     n, h, w, c, x_cs = nhwc_info(x, "x")
     y = out if out is not None else torch.empty((n, h, w, c), dtype=torch.float32, device=x.device)
     _, _, _, _, y_cs = nhwc_info(y, "out")
-    stats = torch.empty((n * (c // cpg) * 2,), dtype=torch.float64, device=x.device)
+    stats = torch.empty((n * (c // cpg) * 3,), dtype=torch.float64, device=x.device)
     _lib.check(_lib.load().mn_groupnorm_swish(_ptr(x), x_cs, _ptr(y), y_cs, _ptr(gamma), _ptr(beta), n, h, w, c, cpg,
                                               eps, 1 if swish else 0, _ptr(valid_w), _ptr(stats), _stream()),
                "mn_groupnorm_swish")
@@ -278,7 +288,7 @@ def adain_concat(prior, feat, win_dev, nc, wp):
     if pn != nc or pw != wp or fh != h or fc != c:
         raise RuntimeError("adain_concat: shape mismatch")
     out = torch.empty((nc, h, wp, 2 * c), dtype=torch.float32, device=feat.device)
-    stats = torch.empty((nc * c * 4,), dtype=torch.float64, device=feat.device)
+    stats = torch.empty((nc * c * 6,), dtype=torch.float64, device=feat.device)
     _lib.check(_lib.load().mn_adain_concat(_ptr(prior), p_cs, _ptr(feat), f_cs, _ptr(win_dev), _ptr(out), nc, h, wp, w, c,
                                            _ptr(stats), _stream()), "mn_adain_concat")
     LAUNCHES += 3

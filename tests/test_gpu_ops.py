@@ -264,6 +264,17 @@ def test_layernorm_tokenmix_attention():
         _close(ops.attention(qkv.to(d)).cpu(), ref, 2e-5, f"attention S={s}")
 
 
+@pytest.mark.parametrize("m,k,n", [(64, 512, 512), (16, 512, 1536), (64, 1024, 512), (2, 512, 6736), (33, 64, 16)])
+def test_linear_small_m(m, k, n):
+    from marconet_b200 import ops
+    d = _dev()
+    x, w, b, r = _rand(m, k, seed=70), _rand(k, n, seed=71, scale=k ** -0.5), _rand(n, seed=72), _rand(m, n, seed=73)
+    y = ops.linear(x.to(d), w.to(d), b.to(d), act=ops.ACT_GELU, gain=1.5, residual=r.to(d))
+    _close(y.cpu(), F.gelu(x @ w + b + r) * 1.5, 2e-5, f"linear {m}x{k}x{n}")
+    y = ops.linear(x.to(d), w.to(d))
+    _close(y.cpu(), x @ w, 2e-5)
+
+
 def test_layout_roundtrip():
     from marconet_b200 import ops
     d = _dev()
