@@ -16,8 +16,12 @@
 //     ~1000 XU cycles per 768-cycle MMA block (measured: XU 53 % busy, tensor pipe 12 %).  Four dedicated warps now split
 //     each halo tile ONCE per channel block, in place in shared memory (hi plane over box 0, lo plane over box 1, same
 //     XOR swizzle), and the four TMEM-feeding warps only copy shifted rows smem -> TMEM per tap (no ALU work).
-// Warp roles: 0 = weight (B) TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = TMEM feed + epilogue,
-//             6 = halo TMA producer, 7..10 = split (fp32 halo -> hi/lo fp16 halo).
+//   * OVERLAPPED EPILOGUE.  The split warps (which cover the four TMEM lane quarters) also own the epilogue: after splitting
+//     the first two halo tiles of tile i+1 they drain tile i's accumulators (second half parked in registers so the
+//     MMA warp is released after ~1k cycles), stage through shared memory and store with fully coalesced float4 rows,
+//     while the feed + MMA warps are already working on tile i+1.
+// Warp roles: 0 = weight (B) TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = TMEM feed,
+//             6 = halo TMA producer, 7..10 = split (fp32 halo -> hi/lo fp16 halo) + epilogue.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -158,6 +162,94 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int sidx = (warp - 7) * 32 + lane;
         const bool bf = t.prec == MN_PREC_BF16X3_TC;
         const uint32_t mask = bf ? 0xFFFF0000u : 0xFFFFE000u;
+        // ---- epilogue of one finished tile (these warps cover the four TMEM lane quarters: warp & 3) ----
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const float wscale = t.wscale ? *t.wscale : 1.f;
+        const int tn = r / (t.TH * t.TW);
+        const int rem = r - tn * (t.TH * t.TW);
+        const int th = rem / t.TW, tw = rem - th * t.TW;
+        uint32_t ecnt = 0;
+        auto epilogue = [&](int work) {
+            const int nt_i = work % t.n_tiles;
+            int n0, oy0, ox0;
+            tile_origin(work, n0, oy0, ox0);
+            {
+                const int n = n0 + tn, oy = oy0 + th, ox = ox0 + tw;
+                const bool ok = n < g.N && oy < g.OH && ox < g.OW;
+                rowm[r] = ok ? (n * g.OH + oy) * g.OW + ox : -1;
+                rowm[128 + r] = ok ? (n | ((g.valid_w && ox >= g.valid_w[n]) ? (1 << 30) : 0)) : 0;
+            }
+            mbar_wait(bar(I_ACCF), ecnt & 1);
+            ++ecnt;
+            tc_fence_after();
+            constexpr int HALVES = NT / STG_COLS;
+            float keep[(HALVES > 1) ? STG_COLS : 1];           // second half parked in registers so TMEM is released early
+            auto drain = [&](int half, bool to_regs) {
+#pragma unroll
+                for (int chunk = 0; chunk < STG_COLS / 16; ++chunk) {
+                    uint32_t acc[16];
+                    tc_ld16(lane_addr + half * STG_COLS + chunk * 16, acc);
+                    if (t.prec != MN_PREC_F16X1_TC) {
+                        uint32_t cor[16];
+                        tc_ld16(lane_addr + NT + half * STG_COLS + chunk * 16, cor);
+                        tc_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) acc[i] = __float_as_uint((__uint_as_float(acc[i]) + __uint_as_float(cor[i])) * wscale);
+                    } else {
+                        tc_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) acc[i] = __float_as_uint(__uint_as_float(acc[i]) * wscale);
+                    }
+                    if (to_regs) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) keep[(HALVES > 1) ? chunk * 16 + i : 0] = __uint_as_float(acc[i]);
+                    } else {
+                        float4* dst = reinterpret_cast<float4*>(stg + r * STG_PITCH + chunk * 16);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            dst[i] = make_float4(__uint_as_float(acc[4 * i]), __uint_as_float(acc[4 * i + 1]), __uint_as_float(acc[4 * i + 2]),
+                                                 __uint_as_float(acc[4 * i + 3]));
+                    }
+                }
+            };
+            drain(0, false);
+            if (HALVES > 1) drain(1, true);
+            tc_fence_before();
+            mbar_arrive(bar(I_ACCE));                            // accumulators fully read: the MMA warp may start the next tile
+#pragma unroll 1
+            for (int half = 0; half < HALVES; ++half) {
+                if (half == 1) {
+                    float4* dst = reinterpret_cast<float4*>(stg + r * STG_PITCH);
+#pragma unroll
+                    for (int i = 0; i < STG_COLS / 4; ++i)
+                        dst[i] = make_float4(keep[(HALVES > 1) ? 4 * i : 0], keep[(HALVES > 1) ? 4 * i + 1 : 0], keep[(HALVES > 1) ? 4 * i + 2 : 0],
+                                             keep[(HALVES > 1) ? 4 * i + 3 : 0]);
+                }
+                named_bar_sync(1, 128);
+                {
+                    const int col = (lane & 15) * 4;
+                    const int o = nt_i * NT + half * STG_COLS + col;
+                    const float4 bias4 = g.bias ? ldg4(g.bias + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+                    for (int i = 0; i < 16; ++i) {
+                        const int row = q * 32 + i * 2 + (lane >> 4);
+                        const int m = rowm[row];
+                        if (m >= 0) {
+                            const int nn = rowm[128 + row];
+                            const float4 u = *reinterpret_cast<const float4*>(stg + row * STG_PITCH + col);
+                            conv_epilogue_vec4(g, m, nn & 0x3FFFFFFF, (nn >> 30) != 0, o, u, bias4);
+                        }
+                    }
+                }
+                named_bar_sync(1, 128);
+            }
+        };
+        // The epilogue of tile i runs after the first two halo tiles of tile i+1 have been split, so the feed/MMA warps have
+        // ~2 x taps k-blocks of work queued while these warps drain TMEM and store tile i.
+        const int epi_after_cb = t.cblocks > 1 ? 1 : 0;
+        int prev_work = -1;
         uint32_t hs = 0, hph = 0;
         for (int work = cluster_id; work < total_work; work += num_clusters) {
             for (int cb = 0; cb < t.cblocks; ++cb) {
@@ -196,8 +288,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // these generic writes precede the next TMA refill
                 mbar_arrive(bar(I_SD + hs));
                 hs ^= 1; if (hs == 0) hph ^= 1;
+                if (cb == epi_after_cb && prev_work >= 0) epilogue(prev_work);
             }
+            prev_work = work;
         }
+        if (prev_work >= 0) epilogue(prev_work);
     } else if (warp == 1) {
         // =========================== MMA issuer (whole warp converged, one elected lane issues) ===========================
         const uint32_t fmt = (t.prec == MN_PREC_BF16X3_TC) ? 1u : 0u;
@@ -237,26 +332,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             __syncwarp();
         }
     } else {
-        // =========================== TMEM feed (shifted rows of the split halo -> A operand) + epilogue ===========================
+        // =========================== TMEM feed: shifted rows of the split halo -> A operand ===========================
         const int q = warp & 3;
         const int r = q * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-        const float wscale = t.wscale ? *t.wscale : 1.f;
         const int tn = r / (t.TH * t.TW);
         const int rem = r - tn * (t.TH * t.TW);
         const int th = rem / t.TW, tw = rem - th * t.TW;
         const int rho0 = (tn * t.HHt + th) * t.HWd + tw;       // halo row of tap (0,0) for this output pixel
-        uint32_t hs = 0, hph = 0, as = 0, aph = 0, tcnt = 0;
-        for (int work = cluster_id; work < total_work; work += num_clusters, ++tcnt) {
-            const int nt_i = work % t.n_tiles;
-            int n0, oy0, ox0;
-            tile_origin(work, n0, oy0, ox0);
-            {
-                const int n = n0 + tn, oy = oy0 + th, ox = ox0 + tw;
-                const bool ok = n < g.N && oy < g.OH && ox < g.OW;
-                rowm[r] = ok ? (n * g.OH + oy) * g.OW + ox : -1;
-                rowm[128 + r] = ok ? (n | ((g.valid_w && ox >= g.valid_w[n]) ? (1 << 30) : 0)) : 0;
-            }
+        uint32_t hs = 0, hph = 0, as = 0, aph = 0;
+        for (int work = cluster_id; work < total_work; work += num_clusters) {
             for (int cb = 0; cb < t.cblocks; ++cb) {
                 mbar_wait(bar(I_SD + hs), hph);
                 const uint8_t* halo = smem + hs * t.halo_stage_bytes;
@@ -291,54 +376,6 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 hs ^= 1; if (hs == 0) hph ^= 1;
             }
 
-            // ---- epilogue: TMEM -> registers -> staging smem -> coalesced global stores ----
-            mbar_wait(bar(I_ACCF), tcnt & 1);
-            tc_fence_after();
-#pragma unroll 1
-            for (int half = 0; half < NT / STG_COLS; ++half) {
-#pragma unroll
-                for (int chunk = 0; chunk < STG_COLS / 16; ++chunk) {
-                    uint32_t acc[16];
-                    tc_ld16(lane_addr + half * STG_COLS + chunk * 16, acc);
-                    if (t.prec != MN_PREC_F16X1_TC) {
-                        uint32_t cor[16];
-                        tc_ld16(lane_addr + NT + half * STG_COLS + chunk * 16, cor);
-                        tc_wait_ld();
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) acc[i] = __float_as_uint((__uint_as_float(acc[i]) + __uint_as_float(cor[i])) * wscale);
-                    } else {
-                        tc_wait_ld();
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) acc[i] = __float_as_uint(__uint_as_float(acc[i]) * wscale);
-                    }
-                    float4* dst = reinterpret_cast<float4*>(stg + r * STG_PITCH + chunk * 16);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        dst[i] = make_float4(__uint_as_float(acc[4 * i]), __uint_as_float(acc[4 * i + 1]), __uint_as_float(acc[4 * i + 2]),
-                                             __uint_as_float(acc[4 * i + 3]));
-                }
-                if (half == NT / STG_COLS - 1) {      // accumulators fully read: the MMA warp may start the next tile
-                    tc_fence_before();
-                    mbar_arrive(bar(I_ACCE));
-                }
-                named_bar_sync(1, 128);
-                {
-                    const int col = (lane & 15) * 4;
-                    const int o = nt_i * NT + half * STG_COLS + col;
-                    const float4 bias4 = g.bias ? ldg4(g.bias + o) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-                    for (int i = 0; i < 16; ++i) {
-                        const int row = q * 32 + i * 2 + (lane >> 4);
-                        const int m = rowm[row];
-                        if (m >= 0) {
-                            const int nn = rowm[128 + row];
-                            const float4 u = *reinterpret_cast<const float4*>(stg + row * STG_PITCH + col);
-                            conv_epilogue_vec4(g, m, nn & 0x3FFFFFFF, (nn >> 30) != 0, o, u, bias4);
-                        }
-                    }
-                }
-                named_bar_sync(1, 128);
-            }
         }
     }
     tc_fence_before();
