@@ -43,24 +43,44 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region, in-process through NVML (pynvml), every 20 ms;
+    falls back to polling nvidia-smi when NVML is unavailable."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
     def run(self):
+        n = self.nvml
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([f.strip() for f in out.split(",")])
+                if n is not None:
+                    mhz = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                    r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                    flags = [bool(r & n.nvmlClocksEventReasonHwSlowdown), bool(r & n.nvmlClocksEventReasonHwThermalSlowdown),
+                             bool(r & n.nvmlClocksEventReasonSwThermalSlowdown), bool(r & n.nvmlClocksEventReasonSwPowerCap)]
+                    self.samples.append([str(mhz), str(self.max_mhz)] + ["Active" if f else "Not Active" for f in flags])
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.samples.append([f.strip() for f in out.split(",")])
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.02 if n is not None else 0.2)
 
     def summary(self):
         self.stop_flag.set()
@@ -74,7 +94,8 @@ class ClockSampler(threading.Thread):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
-        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=mx or None, reasons=sorted(reasons), samples=len(sm))
+        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=mx or None, reasons=sorted(reasons), samples=len(sm),
+                    source="nvml" if self.nvml is not None else "nvidia-smi")
 
 
 def make_inputs(lines, chars, seed):
@@ -320,9 +341,16 @@ def modconv_roofline(tspgan, chars, dev, iters=20):
     ms = tot / iters
     flops = 2.0 * 512 * 512 * 9 * 32 * 32 * chars
     achieved = flops / (ms * 1e-3) / 1e12
-    return {"kernel": "mn_conv2d_nhwc modulated 3x3 512->512 @32x32 x%d chars" % chars, "bound": "tensor", "achieved": achieved,
-            "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_burst"], "traffic": None,
-            "ms_per_launch": ms, "peak_source": peaks["source"] + ", bf16 burst (kernel timed alone, L2 flushed)"}
+    passes = {0: 0, 1: 3, 2: 3, 3: 1}[ops.default_precision()]
+    return {"kernel": "mn_conv2d_nhwc modulated 3x3 512->512 @32x32 x%d chars (conv_tc2_kernel<128>)" % chars, "bound": "tensor",
+            "achieved": achieved, "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_burst"],
+            # dram__bytes_read.sum + dram__bytes_write.sum of this launch from profiles/r1_tc2_ncu_full.txt (ncu --set full)
+            "traffic": 46.6e6 if chars == 16 else None,
+            "algorithmic_gflop_per_launch": flops / 1e9, "ms_per_launch": ms,
+            "mma_passes_per_algorithmic_flop": passes,
+            "tensor_pipe_frac": (achieved * passes / peaks["tf_burst"]) if passes else 0.0,
+            "peak_source": peaks["source"] + ", bf16 dense burst (kernel timed alone, L2 flushed between launches); "
+                           "fp32-grade products cost 3 fp16 MMAs each, so the ceiling of this kernel is peak/3 in algorithmic terms"}
 
 
 def main():
