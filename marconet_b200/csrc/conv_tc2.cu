@@ -177,7 +177,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             tile_origin(work, n0, oy0, ox0);
             {
                 const int n = n0 + tn, oy = oy0 + th, ox = ox0 + tw;
-                const bool ok = n < g.N && oy < g.OH && ox < g.OW;
+                const bool ok = tn < t.TN && n < g.N && oy < g.OH && ox < g.OW;
                 rowm[r] = ok ? (n * g.OH + oy) * g.OW + ox : -1;
                 rowm[128 + r] = ok ? (n | ((g.valid_w && ox >= g.valid_w[n]) ? (1 << 30) : 0)) : 0;
             }
@@ -339,7 +339,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int tn = r / (t.TH * t.TW);
         const int rem = r - tn * (t.TH * t.TW);
         const int th = rem / t.TW, tw = rem - th * t.TW;
-        const int rho0 = (tn * t.HHt + th) * t.HWd + tw;       // halo row of tap (0,0) for this output pixel
+        const int rho0 = tn < t.TN ? (tn * t.HHt + th) * t.HWd + tw : 0;   // halo row of tap (0,0); unused MMA rows read row 0
         uint32_t hs = 0, hph = 0, as = 0, aph = 0;
         for (int work = cluster_id; work < total_work; work += num_clusters) {
             for (int cb = 0; cb < t.cblocks; ++cb) {
@@ -429,8 +429,11 @@ Tc2Plan plan_tc2(const ConvGeom& g) {
     t.TN = 128 / (t.TH * t.TW);
     t.ph = g.ph; t.pw = g.pw; t.KW = g.KW;
     t.HHt = t.TH + 2 * g.ph; t.HWd = t.TW + 2 * g.pw;
+    // tiny images (4x4): 8 whole images per tile would need a 288-row halo; use fewer images per tile and leave the upper
+    // TMEM lanes of the 128-row MMA unused (their rows map outside the tensor and are masked in the epilogue).
+    while (t.TN > 1 && t.TN * t.HHt * t.HWd > 208) t.TN >>= 1;
     t.halo_rows = t.TN * t.HHt * t.HWd;
-    if (t.halo_rows > 208) return fail("halo tile too large for shared memory (tiny images: use the split-K fp32 path)");
+    if (t.halo_rows > 208) return fail("halo tile too large for shared memory");
     if (t.HWd > 256 || t.HHt > 256 || t.TN > 256) return fail("TMA box dim");
     t.box_bytes = (t.halo_rows * 128 + 1023) & ~1023;
     t.halo_stage_bytes = 2 * t.box_bytes;

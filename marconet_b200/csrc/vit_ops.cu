@@ -92,45 +92,48 @@ __global__ void __launch_bounds__(256) attention_kernel(const float* __restrict_
     }
 }
 
-// Small-M linear layer (M <= 64 rows: the 64 / 16 tokens of one text line): y = act(x W + b) * gain + residual.
-// One block = all M rows x 16 output columns, K streamed in 32-wide chunks with register-prefetched double buffering.
+// Small-M linear layer (M <= 64 rows: the 64 / 16 tokens of one text line): y = act(x W + b + residual) * gain.
+// One block = all M rows x 16 output columns; K is streamed in 32-wide chunks through a 4-stage cp.async ring so that
+// four chunks of weights are in flight per block (the layer is pure HBM/L2 latency: 32..421 blocks, 2 KB of W per chunk).
 // No split-K, no second pass: the TextViT's ~45 GEMMs per line are launch/latency bound, not FLOP bound.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
 __global__ void __launch_bounds__(128) linear_small_m_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                              const float* __restrict__ bias, const float* __restrict__ residual,
                                                              float* __restrict__ y, int M, int K, int N, int act, float gain) {
-    __shared__ __align__(16) float Xs[2][64][36];
-    __shared__ __align__(16) float Ws[2][32][16];
+    constexpr int ST = 4;
+    __shared__ __align__(16) float Xs[ST][64][36];
+    __shared__ __align__(16) float Ws[ST][32][16];
     const int tid = threadIdx.x;
     const int col = tid & 15, rg = tid >> 4;            // 16 columns x 8 row groups of 8 rows
     const int n0 = blockIdx.x * 16;
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    float4 xr[4], wr;
-    auto gload = [&](int k0) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {                   // X chunk: 64 rows x 32 floats = 512 float4
-            const int idx = tid + i * 128, r = idx >> 3, c4 = (idx & 7) * 4;
-            xr[i] = r < M ? __ldg(reinterpret_cast<const float4*>(x + (size_t)r * K + k0 + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        const int kr = tid >> 2, c4 = (tid & 3) * 4;    // W chunk: 32 rows x 16 floats = 128 float4
-        wr = __ldg(reinterpret_cast<const float4*>(w + (size_t)(k0 + kr) * N + n0 + c4));
-    };
-    auto sstore = [&](int buf) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int idx = tid + i * 128, r = idx >> 3, c4 = (idx & 7) * 4;
-            *reinterpret_cast<float4*>(&Xs[buf][r][c4]) = xr[i];
-        }
-        *reinterpret_cast<float4*>(&Ws[buf][tid >> 2][(tid & 3) * 4]) = wr;
-    };
     const int nchunks = K / 32;
-    gload(0);
-    sstore(0);
-    __syncthreads();
+    auto issue = [&](int ch) {
+        if (ch < nchunks) {
+            const int k0 = ch * 32, buf = ch % ST;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {               // X chunk: 64 rows x 32 floats = 512 x 16 B
+                const int idx = tid + i * 128, r = idx >> 3, c4 = (idx & 7) * 4;
+                cp_async16(&Xs[buf][r][c4], x + (size_t)(r < M ? r : 0) * K + k0 + c4, r < M);
+            }
+            const int kr = tid >> 2, c4 = (tid & 3) * 4; // W chunk: 32 rows x 16 floats = 128 x 16 B
+            cp_async16(&Ws[buf][kr][c4], w + (size_t)(k0 + kr) * N + n0 + c4, true);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+#pragma unroll
+    for (int s = 0; s < ST - 1; ++s) issue(s);
     for (int ch = 0; ch < nchunks; ++ch) {
-        const int buf = ch & 1;
-        if (ch + 1 < nchunks) gload((ch + 1) * 32);
+        issue(ch + ST - 1);
+        asm volatile("cp.async.wait_group %0;" ::"n"(ST - 1) : "memory");
+        __syncthreads();
+        const int buf = ch % ST;
 #pragma unroll
         for (int k4 = 0; k4 < 8; ++k4) {
             const float w0 = Ws[buf][k4 * 4][col], w1 = Ws[buf][k4 * 4 + 1][col], w2 = Ws[buf][k4 * 4 + 2][col], w3 = Ws[buf][k4 * 4 + 3][col];
@@ -141,7 +144,6 @@ __global__ void __launch_bounds__(128) linear_small_m_kernel(const float* __rest
                 acc[i] = fmaf(xv.z, w2, acc[i]); acc[i] = fmaf(xv.w, w3, acc[i]);
             }
         }
-        if (ch + 1 < nchunks) sstore(buf ^ 1);
         __syncthreads();
     }
     const int o = n0 + col;
