@@ -74,6 +74,26 @@ def test_conv_small_cout_direct_kernel(shape):
     _close(_nchw(y), ref, 1e-5, f"small-cout conv {shape}")
 
 
+def test_conv_kernels_are_deterministic_under_repetition():
+    """Race detector: every conv path (direct small-Cout, fp32 implicit GEMM incl. split-K, tcgen05) must return
+    bit-identical results over many back-to-back launches on fresh output buffers."""
+    from marconet_b200 import ops
+    d = _dev()
+    cases = [((2, 13, 45, 64, 3), ops.PREC_FP32_SIMT), ((2, 16, 24, 64, 128), ops.PREC_FP32_SIMT), ((5, 4, 4, 512, 512), ops.PREC_FP32_SIMT),
+             ((3, 32, 32, 64, 256), ops.PREC_F16X3_TC), ((16, 8, 8, 128, 512), ops.PREC_F16X3_TC), ((3, 8, 16, 64, 128), ops.PREC_F16X3_TC)]
+    for (n, h, w, cin, cout), prec in cases:
+        x = _nhwc(_rand(n, cin, h, w, seed=80))
+        wt = ops.ConvWeight(_pack(_rand(cout, cin, 3, 3, seed=81, scale=0.05)), 9)
+        bias = _rand(cout, seed=82).to(d)
+        ref = None
+        for it in range(12):
+            y = ops.conv2d(x, wt, 3, 3, pad=(1, 1), bias=bias, act=ops.ACT_LRELU02, gain=1.1, precision=prec)
+            if ref is None:
+                ref = y.clone()
+            else:
+                assert torch.equal(y, ref), f"non-deterministic result: case {(n, h, w, cin, cout)} prec {prec} iteration {it}"
+
+
 def test_conv_forced_splitk_matches():
     from marconet_b200 import ops
     x = _rand(2, 256, 8, 8, seed=3)
