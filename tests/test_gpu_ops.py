@@ -58,7 +58,7 @@ def test_conv_plain(case):
     x = _rand(n, cin, h, w, seed=1)
     wt = _rand(cout, cin, k, k, seed=2, scale=1.0 / math.sqrt(cin * k * k))
     ref = F.conv2d(x, wt, stride=stride, padding=pad)
-    y = ops.conv2d(_nhwc(x), _pack(wt), k, k, stride=stride, pad=(pad, pad))
+    y = ops.conv2d(_nhwc(x), _pack(wt), k, k, stride=stride, pad=(pad, pad), precision=ops.PREC_FP32_SIMT)   # the exact fp32 kernels
     _close(_nchw(y), ref, 2e-5, f"conv {case}")
 
 
