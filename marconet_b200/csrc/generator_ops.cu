@@ -24,10 +24,10 @@ __global__ void select_text_kernel(const float* __restrict__ emb, const int64_t*
     // out: [N, 4, 4*L, C]; one thread per 4 channels of one output pixel
     const int c4 = C >> 2;
     const int64_t total = (int64_t)N * 16 * L * c4;
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;     // host guarantees total < 2^31: 32-bit div/mod only
+    if (idx >= (uint32_t)total) return;
     const int c = (int)(idx % c4) * 4;
-    int64_t pix = idx / c4;
+    uint32_t pix = idx / c4;
     const int xw = (int)(pix % (4 * L));
     pix /= (4 * L);
     const int n = (int)(pix / 4);
@@ -38,7 +38,7 @@ __global__ void select_text_kernel(const float* __restrict__ emb, const int64_t*
         const float* sn = s + (size_t)n * s_stride + c;
         e.x *= sn[0]; e.y *= sn[1]; e.z *= sn[2]; e.w *= sn[3];
     }
-    *reinterpret_cast<float4*>(out + idx * 4) = e;
+    *reinterpret_cast<float4*>(out + (size_t)idx * 4) = e;
 }
 
 // ---------------------------------------------------------------- demodulation (networks.py:284-287)
@@ -96,10 +96,10 @@ __global__ void resample_modulate_kernel(const float* __restrict__ x, int x_cs, 
     const int OH = up ? 2 * H : H, OW = up ? 2 * W : W;
     const int c4 = C >> 2;
     const int64_t total = (int64_t)N * OH * OW * c4;
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;     // host guarantees total < 2^31: 32-bit div/mod only
+    if (idx >= (uint32_t)total) return;
     const int c = (int)(idx % c4) * 4;
-    int64_t pix = idx / c4;
+    uint32_t pix = idx / c4;
     const int ox = (int)(pix % OW);
     pix /= OW;
     const int oy = (int)(pix % OH);
@@ -199,6 +199,7 @@ extern "C" int mn_select_text(const float* emb, const int64_t* labels, const flo
                               float* out, int N, int L, int C, void* stream) {
     MN_REQUIRE(emb && labels && out && N > 0 && L > 0 && C > 0 && (C & 3) == 0, "mn_select_text: bad args");
     const int64_t total = (int64_t)N * 16 * L * (C >> 2);
+    MN_REQUIRE(total < (1ll << 31), "tensor too large for 32-bit indexing");
     select_text_kernel<<<(unsigned)mn_cdiv64(total, 256), 256, 0, (cudaStream_t)stream>>>(emb, labels, s, s_stride, out, N, L, C);
     MN_LAUNCH_CHECK();
     return MN_OK;
@@ -219,6 +220,7 @@ extern "C" int mn_resample_modulate(const float* x, int x_cs, float* y, int y_cs
     MN_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0, "mn_resample_modulate: pointers must be 16B aligned");
     const int OH = up ? 2 * H : H, OW = up ? 2 * W : W;
     const int64_t total = (int64_t)N * OH * OW * (C >> 2);
+    MN_REQUIRE(total < (1ll << 31), "tensor too large for 32-bit indexing");
     resample_modulate_kernel<<<(unsigned)mn_cdiv64(total, 256), 256, 0, (cudaStream_t)stream>>>(x, x_cs, y, y_cs, s, s_stride, N, H, W, C, up);
     MN_LAUNCH_CHECK();
     return MN_OK;

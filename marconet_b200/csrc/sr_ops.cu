@@ -71,19 +71,19 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, int x_cs, float* __
                                 const int32_t* __restrict__ valid_w, const float2* __restrict__ mr) {
     const int c4 = C >> 2;
     const int64_t total = (int64_t)N * H * W * c4;
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;     // host guarantees total < 2^31: 32-bit div/mod only
+    if (idx >= (uint32_t)total) return;
     const int c = (int)(idx % c4) * 4;
-    const int64_t pix = idx / c4;
+    const uint32_t pix = idx / c4;
     const int px = (int)(pix % W);
-    const int n = (int)(pix / ((int64_t)H * W));
+    const int n = (int)(pix / (uint32_t)(H * W));
     const int wv = valid_w ? valid_w[n] : W;
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
     if (px < wv) {
         const int G = C / cpg, g = c / cpg;
         const float2 m2 = mr[(size_t)n * G + g];
         const float mean = m2.x, rstd = m2.y;
-        const float4 v = *reinterpret_cast<const float4*>(x + pix * x_cs + c);
+        const float4 v = *reinterpret_cast<const float4*>(x + (size_t)pix * x_cs + c);
         const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
         const float gam[4] = {ga.x, ga.y, ga.z, ga.w}, bet[4] = {be.x, be.y, be.z, be.w};
         float t[4] = {v.x, v.y, v.z, v.w};
@@ -95,7 +95,7 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, int x_cs, float* __
         }
         o = make_float4(t[0], t[1], t[2], t[3]);
     }
-    *reinterpret_cast<float4*>(y + pix * y_cs + c) = o;
+    *reinterpret_cast<float4*>(y + (size_t)pix * y_cs + c) = o;
 }
 
 // ---------------------------------------------------------------- AdaIN + concat
@@ -174,13 +174,13 @@ __global__ void adain_apply_kernel(const float* __restrict__ prior, int prior_cs
                                    int Nc, int H, int Wp, int W, int C) {
     const int c4 = C >> 2;
     const int64_t total = (int64_t)Nc * H * Wp * c4;
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;     // host guarantees total < 2^31: 32-bit div/mod only
+    if (idx >= (uint32_t)total) return;
     const int c = (int)(idx % c4) * 4;
-    int64_t pix = idx / c4;
+    uint32_t pix = idx / c4;
     const int xx = (int)(pix % Wp);
     const int yy = (int)((pix / Wp) % H);
-    const int i = (int)(pix / ((int64_t)Wp * H));
+    const int i = (int)(pix / (uint32_t)(Wp * H));
     const mn_window wn = win[i];
     const int wv = wn.x2 - wn.x1;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
@@ -195,7 +195,7 @@ __global__ void adain_apply_kernel(const float* __restrict__ prior, int prior_cs
         }
         a = make_float4(o[0], o[1], o[2], o[3]);
     }
-    float* op = out + pix * (2 * C);
+    float* op = out + (size_t)pix * (2 * C);
     *reinterpret_cast<float4*>(op + c) = a;
     *reinterpret_cast<float4*>(op + C + c) = b;
 }
@@ -207,14 +207,14 @@ __global__ void window_scatter_kernel(const float* __restrict__ feat, int feat_c
                                       int B, int H, int W, int Wp, int C) {
     const int c4 = C >> 2;
     const int64_t total = (int64_t)B * H * W * c4;
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;     // host guarantees total < 2^31: 32-bit div/mod only
+    if (idx >= (uint32_t)total) return;
     const int c = (int)(idx % c4) * 4;
-    const int64_t pix = idx / c4;
+    const uint32_t pix = idx / c4;
     const int x = (int)(pix % W);
     const int y = (int)((pix / W) % H);
-    const int b = (int)(pix / ((int64_t)H * W));
-    const float4 f = *reinterpret_cast<const float4*>(feat + pix * feat_cs + c);
+    const int b = (int)(pix / (uint32_t)(H * W));
+    const float4 f = *reinterpret_cast<const float4*>(feat + (size_t)pix * feat_cs + c);
     float4 o = f;
     const int i = owner[(size_t)b * W + x];
     if (i >= 0) {
@@ -227,7 +227,7 @@ __global__ void window_scatter_kernel(const float* __restrict__ feat, int feat_c
         o.z = __fadd_rn(f.z, __fadd_rn(__fmul_rn(f.z, sc.z), sh.z));
         o.w = __fadd_rn(f.w, __fadd_rn(__fmul_rn(f.w, sc.w), sh.w));
     }
-    *reinterpret_cast<float4*>(out + pix * out_cs + c) = o;
+    *reinterpret_cast<float4*>(out + (size_t)pix * out_cs + c) = o;
 }
 
 }  // namespace
@@ -255,6 +255,7 @@ extern "C" int mn_groupnorm_swish(const float* x, int x_cs, float* y, int y_cs, 
     gn_finalize_kernel<<<mn_cdiv(N * G, 128), 128, 0, st>>>(stats_ws, mr, N, G, H, W, cpg, eps, valid_w);
     MN_LAUNCH_CHECK();
     const int64_t total = (int64_t)N * H * W * (C >> 2);
+    MN_REQUIRE(total < (1ll << 31), "tensor too large for 32-bit indexing");
     gn_apply_kernel<<<(unsigned)mn_cdiv64(total, 256), 256, 0, st>>>(x, x_cs, y, y_cs, gamma, beta, N, H, W, C, cpg, eps, swish, valid_w, mr);
     MN_LAUNCH_CHECK();
     return MN_OK;
@@ -280,6 +281,7 @@ extern "C" int mn_adain_concat(const float* prior, int prior_cs, const float* fe
     adain_finalize_kernel<<<mn_cdiv(Nc * C, 256), 256, 0, st>>>(stats_ws, win, ms, Nc, C, H);
     MN_LAUNCH_CHECK();
     const int64_t total = (int64_t)Nc * H * Wp * (C >> 2);
+    MN_REQUIRE(total < (1ll << 31), "tensor too large for 32-bit indexing");
     adain_apply_kernel<<<(unsigned)mn_cdiv64(total, 256), 256, 0, st>>>(prior, prior_cs, feat, feat_cs, win, ms, out, Nc, H, Wp, W, C);
     MN_LAUNCH_CHECK();
     return MN_OK;
@@ -291,6 +293,7 @@ extern "C" int mn_window_scatter(const float* feat, int feat_cs, const float* sc
     MN_REQUIRE(feat && scale && shift && owner && win && out, "mn_window_scatter: null pointer");
     MN_REQUIRE(B > 0 && H > 0 && W > 0 && Wp > 0 && (C & 3) == 0 && (feat_cs & 3) == 0 && (out_cs & 3) == 0, "mn_window_scatter: bad dims");
     const int64_t total = (int64_t)B * H * W * (C >> 2);
+    MN_REQUIRE(total < (1ll << 31), "tensor too large for 32-bit indexing");
     window_scatter_kernel<<<(unsigned)mn_cdiv64(total, 256), 256, 0, (cudaStream_t)stream>>>(feat, feat_cs, scale, shift, owner, win, out, out_cs, B, H, W, Wp, C);
     MN_LAUNCH_CHECK();
     return MN_OK;
