@@ -219,12 +219,14 @@ def run_ours(args):
     lab_dev = [l.to(dev) for l in labels]
     lq_dev, locs_dev = lq_pin.to(dev), locs_pin.to(dev)
 
+    lab_all = torch.cat(lab_dev, dim=0)
+
     def step(lq, locs):
         _, _, w = nets["encoder"](lq)
-        p64, p32 = [], []
-        for b in range(lines):
-            _, f64, f32_ = nets["tspgan"](styles=w[b:b + 1].expand(chars, -1), labels=lab_dev[b], noise=None)
-            p64.append(f64); p32.append(f32_)
+        # one generator call for the characters of all lines of the step (per-character style = its line's w), then per-line views
+        _, f64, f32_ = nets["tspgan"](styles=w.repeat_interleave(chars, dim=0), labels=lab_all, noise=None)
+        p64 = [f64[b * chars:(b + 1) * chars] for b in range(lines)]
+        p32 = [f32_[b * chars:(b + 1) * chars] for b in range(lines)]
         return nets["sr"](lq, p64, p32, locs)
 
     def barrier():

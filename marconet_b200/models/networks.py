@@ -475,7 +475,17 @@ class TSPSRNet(_PackedModule):
             if p.dim() != 4 or p.shape[1] != channels or p.shape[2] != size or p.shape[3] != size:
                 raise RuntimeError(f"prior has shape {tuple(p.shape)}, expected [n,{channels},{size},{size}]")
             views.append(ops.as_nhwc(p.float()))
-        return views[0] if len(views) == 1 else torch.cat(views, dim=0)
+        if len(views) == 1:
+            return views[0]
+        # priors of consecutive lines that are slices of ONE generator call are already adjacent in memory: re-join them
+        # without a copy; anything else is concatenated.
+        nxt, total = views[0].data_ptr(), 0
+        for v in views:
+            if not v.is_contiguous() or v.data_ptr() != nxt or v.untyped_storage().data_ptr() != views[0].untyped_storage().data_ptr():
+                return torch.cat(views, dim=0)
+            nxt += v.numel() * 4
+            total += v.shape[0]
+        return torch.as_strided(views[0], (total,) + tuple(views[0].shape[1:]), views[0].stride())
 
     @torch.no_grad()
     def forward(self, lq, priors64, priors32, locs):
