@@ -317,15 +317,9 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def modconv_roofline(tspgan, chars, dev, iters=20):
-    """Live CUDA-event timing of the dominant kernel: the 3x3 modulated conv 512->512 at 32x32 for `chars`
-    characters (reference networks.py:294,299 grouped conv; 4.83 GFLOP per character and launch)."""
+def _time_modconv(e, chars, dev, iters):
     import torch
     from marconet_b200 import ops
-    peaks = load_peaks()
-    gen = tspgan.TextGenerator
-    pk = gen._get_packed(dev)
-    e = pk["styled"][6]                                   # convs.5: 512->512 @ 32x32, no upsample
     x = torch.randn(chars, 32, 32, 512, device=dev)
     dm = torch.rand(chars, 512, device=dev) + 0.5
     flush = torch.empty(64 << 20, dtype=torch.float32, device=dev)   # 256 MB > L2
@@ -341,8 +335,21 @@ def modconv_roofline(tspgan, chars, dev, iters=20):
         if i >= 3:
             tot += e0.elapsed_time(e1)
     ms = tot / iters
-    flops = 2.0 * 512 * 512 * 9 * 32 * 32 * chars
+    return ms, 2.0 * 512 * 512 * 9 * 32 * 32 * chars
+
+
+def modconv_roofline(tspgan, chars, dev, iters=20):
+    """Live CUDA-event timing of the dominant kernel: the 3x3 modulated conv 512->512 at 32x32 for `chars`
+    characters (reference networks.py:294,299 grouped conv; 4.83 GFLOP per character and launch)."""
+    from marconet_b200 import ops
+    peaks = load_peaks()
+    gen = tspgan.TextGenerator
+    pk = gen._get_packed(dev)
+    e = pk["styled"][6]                                   # convs.5: 512->512 @ 32x32, no upsample
+    ms, flops = _time_modconv(e, chars, dev, iters)
     achieved = flops / (ms * 1e-3) / 1e12
+    ms_big, flops_big = _time_modconv(e, 128, dev, 5)     # same kernel with 128 characters: 27.7 waves instead of 3.46
+    big = flops_big / (ms_big * 1e-3) / 1e12
     passes = {0: 0, 1: 3, 2: 3, 3: 1}[ops.default_precision()]
     return {"kernel": "mn_conv2d_nhwc modulated 3x3 512->512 @32x32 x%d chars (conv_tc2_kernel<128>)" % chars, "bound": "tensor",
             "achieved": achieved, "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_burst"],
@@ -351,6 +358,8 @@ def modconv_roofline(tspgan, chars, dev, iters=20):
             "algorithmic_gflop_per_launch": flops / 1e9, "ms_per_launch": ms,
             "mma_passes_per_algorithmic_flop": passes,
             "tensor_pipe_frac": (achieved * passes / peaks["tf_burst"]) if passes else 0.0,
+            "same_kernel_128_chars": {"achieved": big, "frac": big / peaks["tf_burst"], "ms_per_launch": ms_big,
+                                      "tensor_pipe_frac": (big * passes / peaks["tf_burst"]) if passes else 0.0},
             "peak_source": peaks["source"] + ", bf16 dense burst (kernel timed alone, L2 flushed between launches); "
                            "fp32-grade products cost 3 fp16 MMAs each, so the ceiling of this kernel is peak/3 in algorithmic terms"}
 
