@@ -195,6 +195,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const bool row_ok = n < g.N && oy < g.OH && ox < g.OW;
         const int m = (n * g.OH + oy) * g.OW + ox;
         const float wscale = t.wscale ? *t.wscale : 1.f;
+        const float dfix = 1.f + 1.5e-8f * (float)(num_kb * (KB / 16));   // expected truncation shrink of the main accumulator, see conv_tc2.cu
 #pragma unroll 1
         for (int chunk = 0; chunk < NT / 16; ++chunk) {
             uint32_t acc[16];
@@ -204,7 +205,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tc_ld16(lane_addr + NT + chunk * 16, cor);
                 tc_wait_ld();
 #pragma unroll
-                for (int i = 0; i < 16; ++i) acc[i] = __float_as_uint(__uint_as_float(acc[i]) + __uint_as_float(cor[i]));
+                for (int i = 0; i < 16; ++i) acc[i] = __float_as_uint(fmaf(__uint_as_float(acc[i]), dfix, __uint_as_float(cor[i])));
             } else {
                 tc_wait_ld();
             }
