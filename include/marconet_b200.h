@@ -91,6 +91,12 @@ typedef struct {
     /* tensor-core precisions only: weights pre-split by mn_conv_pack_weights_tc()                */
     const void* w_tc_hi; const void* w_tc_lo;  /* 16-bit [KH*KW][Cout][Cin] (K-major)            */
     const float* w_tc_scale;                   /* the 2-float scale record written by the packer */
+    /* optional input transform fused into the tcgen05 v2 kernel's operand-split stage (mn_conv2d_tc_version() == 2 only):
+     *   x' = swish( (x - mean[n,g]) * rstd[n,g] * gamma[c] + beta[c] ),  zero outside the image / beyond valid_w[n]
+     * i.e. GroupNorm(32 channels per group) + swish of models/networks.py:508-512 applied while the A operand is built.  */
+    const float* gn_mean_rstd;                 /* [N][Cin/32][2] from mn_groupnorm_stats, or NULL                          */
+    const float* gn_gamma; const float* gn_beta;   /* [Cin]                                                                */
+    int gn_swish;
 } mn_conv_params;
 
 int mn_conv2d_nhwc(const mn_conv_params* p, void* stream);
@@ -99,6 +105,8 @@ int64_t mn_conv2d_workspace_bytes(const mn_conv_params* p);
 /* 1 if the tcgen05 path can run this geometry (stride 1, 3x3/pad1 or 1x1, Cin%64==0, Cout%64==0,
  * pixel tiles of 128 that tile [N,H,W] exactly); 0 otherwise (mn_last_error() says why). */
 int mn_conv2d_tc_supported(const mn_conv_params* p);
+/* 2: the tcgen05 v2 kernel (halo tiles, fused input transforms) runs this problem; 1: only the v1 kernel; 0: neither. */
+int mn_conv2d_tc_version(const mn_conv_params* p);
 /* Split fp32 weights w:[taps*Cin][Cout] (the layout mn_conv2d_nhwc takes) into hi/lo 16-bit planes
  * [taps][Cout][Cin], pre-scaled by a power of two so the lo plane stays in the fp16 normal range.
  * hi, lo: taps*Cin*Cout 16-bit elements each; scale2: 2 floats {abs-max, 2^-S}. */
@@ -156,6 +164,13 @@ int mn_torgb(const float* x, int x_cs, const float* s, int s_stride, const float
 int mn_groupnorm_swish(const float* x, int x_cs, float* y, int y_cs, const float* gamma, const float* beta,
                        int N, int H, int W, int C, int cpg, float eps, int swish,
                        const int32_t* valid_w, double* stats_ws, void* stream);
+/* The two halves of mn_groupnorm_swish, for fusing the normalisation into the consuming convolution:
+ * statistics -> mean_rstd [N][C/cpg][2] fp32 (stats_ws: >= 2*N*(C/cpg) doubles), and the elementwise apply. */
+int mn_groupnorm_stats(const float* x, int x_cs, int N, int H, int W, int C, int cpg, float eps,
+                       const int32_t* valid_w, double* stats_ws, float* mean_rstd, void* stream);
+int mn_groupnorm_apply(const float* x, int x_cs, float* y, int y_cs, const float* gamma, const float* beta,
+                       const float* mean_rstd, int N, int H, int W, int C, int cpg, int swish,
+                       const int32_t* valid_w, void* stream);
 
 /* Per-character window table entry (host computes the integers bit-exactly like
  * models/networks.py:426-441 / :460-474). */

@@ -32,6 +32,7 @@ class ConvParams(Structure):
         ("split_k", c_int),
         ("precision", c_int),
         ("w_tc_hi", c_void_p), ("w_tc_lo", c_void_p), ("w_tc_scale", c_void_p),
+        ("gn_mean_rstd", c_void_p), ("gn_gamma", c_void_p), ("gn_beta", c_void_p), ("gn_swish", c_int),
     ]
 
 
@@ -51,6 +52,10 @@ SYMBOLS = {
     "mn_conv2d_nhwc": (c_int, [POINTER(ConvParams), c_void_p]),
     "mn_conv2d_workspace_bytes": (c_int64, [POINTER(ConvParams)]),
     "mn_conv2d_tc_supported": (c_int, [POINTER(ConvParams)]),
+    "mn_conv2d_tc_version": (c_int, [POINTER(ConvParams)]),
+    "mn_groupnorm_stats": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mn_groupnorm_apply": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                   c_void_p, c_void_p]),
     "mn_conv_pack_weights_tc": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mn_pixelnorm": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "mn_select_text": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),

@@ -19,6 +19,8 @@ static int make_geom(const mn_conv_params* p, ConvGeom& g) {
     g.x = p->x; g.w = p->w; g.y = p->y; g.y2 = p->y2;
     g.bias = p->bias; g.out_scale = p->out_scale; g.residual = p->residual; g.y2_scale = p->y2_scale;
     g.valid_w = p->valid_w; g.ws = p->workspace;
+    g.gn_mr = reinterpret_cast<const float2*>(p->gn_mean_rstd); g.gn_gamma = p->gn_gamma; g.gn_beta = p->gn_beta; g.gn_swish = p->gn_swish;
+    MN_REQUIRE(!p->gn_mean_rstd || (p->gn_gamma && p->gn_beta && p->Cin % 32 == 0), "mn_conv2d_nhwc: fused GroupNorm needs gamma, beta and Cin % 32 == 0");
     g.N = p->N; g.H = p->H; g.W = p->W; g.Cin = p->Cin; g.x_cs = p->x_cs;
     g.KH = p->KH; g.KW = p->KW; g.sh = p->stride_h; g.sw = p->stride_w; g.ph = p->pad_h; g.pw = p->pad_w; g.Cout = p->Cout;
     g.OH = (p->H + 2 * p->pad_h - p->KH) / p->stride_h + 1;
@@ -50,6 +52,11 @@ extern "C" int mn_conv2d_nhwc(const mn_conv_params* p, void* stream) {
     int rc = make_geom(p, g);
     if (rc != MN_OK) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool v2 = p->precision != MN_PREC_FP32_SIMT && !tc_force_v1() && mn_conv_tc2_supported(g, nullptr);
+    if (g.gn_mr && !v2) {
+        mn_set_error("mn_conv2d_nhwc: the fused GroupNorm input transform exists only in the tcgen05 v2 kernel (check mn_conv2d_tc_version)");
+        return MN_ERR_UNSUPPORTED;
+    }
     switch (p->precision) {
         case MN_PREC_FP32_SIMT:
             if (mn_conv_small_supported(g)) return mn_conv_small_launch(g, st);
@@ -74,4 +81,11 @@ extern "C" int mn_conv2d_tc_supported(const mn_conv_params* p) {
     const int ok = (!tc_force_v1() && mn_conv_tc2_supported(g, nullptr)) || mn_conv_tc_supported(g, &why);
     if (!ok) mn_set_error("tensor-core path unsupported: %s", why);
     return ok;
+}
+
+extern "C" int mn_conv2d_tc_version(const mn_conv_params* p) {
+    ConvGeom g;
+    if (make_geom(p, g) != MN_OK) return 0;
+    if (!tc_force_v1() && mn_conv_tc2_supported(g, nullptr)) return 2;
+    return mn_conv_tc_supported(g, nullptr) ? 1 : 0;
 }

@@ -7,6 +7,7 @@ struct ConvGeom {
     float* y; float* y2;
     const float* bias; const float* out_scale; const float* residual; const float* y2_scale;
     const int32_t* valid_w; float* ws;
+    const float2* gn_mr; const float* gn_gamma; const float* gn_beta; int gn_swish;   // fused GroupNorm(+swish) on the input (tc2 only)
     int N, H, W, Cin, x_cs;
     int KH, KW, sh, sw, ph, pw, Cout;
     int OH, OW, y_cs, y2_cs, res_cs, res_bcast, os_stride, y2s_stride;

@@ -69,9 +69,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t off_b = 2 * t.halo_stage_bytes;
     const uint32_t off_stg = off_b + t.bstages * B_STAGE;
     const uint32_t off_rowm = off_stg + STG_BYTES;
-    const uint32_t off_bars = off_rowm + 1024;
+    const uint32_t off_gnp = off_rowm + 1024;
+    const uint32_t off_bars = off_gnp + 512;
     float* stg = reinterpret_cast<float*>(smem + off_stg);
     int* rowm = reinterpret_cast<int*>(smem + off_rowm);
+    float* gnp = reinterpret_cast<float*>(smem + off_gnp);       // gamma[64] | beta[64] of the current channel block (fused GroupNorm)
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + off_bars);
     // barrier indices
     constexpr int I_HF = 0, I_HE = 2, I_BF = 4, I_BE = 4 + MAX_BSTAGES, I_CD = 4 + 2 * MAX_BSTAGES, I_AE = I_CD + A_STAGES,
@@ -255,8 +257,18 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int epi_after_cb = t.cblocks > 1 ? 1 : 0;
         int prev_work = -1;
         uint32_t hs = 0, hph = 0;
+        const bool gn = g.gn_mr != nullptr;
+        const int G = g.Cin >> 5;
         for (int work = cluster_id; work < total_work; work += num_clusters) {
+            int hn0 = 0, hoy0 = 0, hox0 = 0;
+            if (gn) tile_origin(work, hn0, hoy0, hox0);
             for (int cb = 0; cb < t.cblocks; ++cb) {
+                if (gn) {   // per-channel affine of this 64-channel block -> smem (the previous block's readers are past their rows)
+                    named_bar_sync(2, 128);
+                    if (sidx < 64) gnp[sidx] = g.gn_gamma[cb * KB + sidx];
+                    else gnp[sidx] = g.gn_beta[cb * KB + sidx - 64];
+                    named_bar_sync(2, 128);
+                }
                 mbar_wait(bar(I_HF + hs), hph);
                 uint8_t* halo = smem + hs * t.halo_stage_bytes;
                 for (int rho = sidx; rho < t.halo_rows; rho += 128) {
@@ -264,12 +276,40 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     uint8_t* row1 = row0 + t.box_bytes;
                     const int sw = rho & 7;
                     uint32_t hi[32], lo[32];
+                    // fused GroupNorm(+swish): which pixel is this halo row, is it inside the image / the valid window?
+                    bool inside = true;
+                    float m0 = 0.f, r0 = 1.f, m1 = 0.f, r1 = 1.f;
+                    if (gn) {
+                        const int htn = rho / (t.HHt * t.HWd);
+                        const int hrem = rho - htn * (t.HHt * t.HWd);
+                        const int hy = hrem / t.HWd, hx = hrem - hy * t.HWd;
+                        const int n = hn0 + htn, y = hoy0 - t.ph + hy, x = hox0 - t.pw + hx;
+                        inside = n < g.N && (unsigned)y < (unsigned)g.H && (unsigned)x < (unsigned)g.W && (!g.valid_w || x < g.valid_w[n]);
+                        if (inside) {
+                            const float2 a = g.gn_mr[(size_t)n * G + cb * 2], b2 = g.gn_mr[(size_t)n * G + cb * 2 + 1];
+                            m0 = a.x; r0 = a.y; m1 = b2.x; r1 = b2.y;
+                        }
+                    }
 #pragma unroll
                     for (int box = 0; box < 2; ++box) {
                         const uint8_t* bsrc = box ? row1 : row0;
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const float4 v = *reinterpret_cast<const float4*>(bsrc + ((j ^ sw) << 4));
+                            float4 v = *reinterpret_cast<const float4*>(bsrc + ((j ^ sw) << 4));
+                            if (gn) {
+                                const float mean = box ? m1 : m0, rstd = box ? r1 : r0;
+                                const float4 ga = *reinterpret_cast<const float4*>(&gnp[box * 32 + j * 4]);
+                                const float4 be = *reinterpret_cast<const float4*>(&gnp[64 + box * 32 + j * 4]);
+                                float tt[4] = {v.x, v.y, v.z, v.w};
+                                const float gg[4] = {ga.x, ga.y, ga.z, ga.w}, bb[4] = {be.x, be.y, be.z, be.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    float u = (tt[e] - mean) * rstd * gg[e] + bb[e];
+                                    if (g.gn_swish) u = u * (1.f / (1.f + expf(-u)));
+                                    tt[e] = inside ? u : 0.f;
+                                }
+                                v = make_float4(tt[0], tt[1], tt[2], tt[3]);
+                            }
                             const float h0 = __uint_as_float(__float_as_uint(v.x) & mask), h1 = __uint_as_float(__float_as_uint(v.y) & mask);
                             const float h2 = __uint_as_float(__float_as_uint(v.z) & mask), h3 = __uint_as_float(__float_as_uint(v.w) & mask);
                             const int c = box * 16 + j * 2;
@@ -454,7 +494,7 @@ Tc2Plan plan_tc2(const ConvGeom& g) {
     if (t.cs != 1 && t.cs != 2 && t.cs != 4) t.cs = 1;
     if ((p.NT / t.cs) % 8 != 0) t.cs = 1;
     t.m_groups = (t.m_tiles + t.cs - 1) / t.cs;
-    const int fixed = 2 * t.halo_stage_bytes + STG_BYTES + 1024 + 256 + 1024;
+    const int fixed = 2 * t.halo_stage_bytes + STG_BYTES + 1024 + 512 + 256 + 1024;
     int bs = (SMEM_LIMIT - fixed) / (2 * p.NT * 128);
     if (bs > MAX_BSTAGES) bs = MAX_BSTAGES;
     if (bs < 2) return fail("not enough shared memory for 2 weight stages");

@@ -232,18 +232,22 @@ __global__ void window_scatter_kernel(const float* __restrict__ feat, int feat_c
 
 }  // namespace
 
-extern "C" int mn_groupnorm_swish(const float* x, int x_cs, float* y, int y_cs, const float* gamma, const float* beta,
-                                  int N, int H, int W, int C, int cpg, float eps, int swish,
-                                  const int32_t* valid_w, double* stats_ws, void* stream) {
-    MN_REQUIRE(x && y && gamma && beta && stats_ws, "mn_groupnorm_swish: null pointer");
-    MN_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && cpg > 0 && C % cpg == 0 && cpg % 32 == 0, "mn_groupnorm_swish: bad dims (cpg must be a multiple of 32)");
-    MN_REQUIRE((C & 3) == 0 && (x_cs & 3) == 0 && (y_cs & 3) == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0,
-               "mn_groupnorm_swish: alignment");
+static int gn_check(const float* x, int x_cs, int N, int H, int W, int C, int cpg) {
+    MN_REQUIRE(x && N > 0 && H > 0 && W > 0 && C > 0, "groupnorm: bad dims");
+    MN_REQUIRE(cpg == 32 && C % 32 == 0 && (256 % (C >> 2)) == 0 && C <= 1024, "groupnorm: needs 32 channels per group and C/4 dividing 256");
+    MN_REQUIRE((x_cs & 3) == 0 && ((uintptr_t)x & 15) == 0, "groupnorm: alignment");
+    return MN_OK;
+}
+
+extern "C" int mn_groupnorm_stats(const float* x, int x_cs, int N, int H, int W, int C, int cpg, float eps,
+                                  const int32_t* valid_w, double* stats_ws, float* mean_rstd, void* stream) {
+    int rc = gn_check(x, x_cs, N, H, W, C, cpg);
+    if (rc != MN_OK) return rc;
+    MN_REQUIRE(stats_ws && mean_rstd, "mn_groupnorm_stats: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     const int G = C / cpg;
     MN_CUDA_CHECK(cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * N * G, st));
     const int HW = H * W;
-    MN_REQUIRE(cpg == 32 && (256 % (C >> 2)) == 0 && C <= 1024, "mn_groupnorm_swish: needs 32 channels per group and C/4 dividing 256");
     int blocks = mn_cdiv(mn_num_sms() * 8, N);
     if (blocks > mn_cdiv(HW, 64)) blocks = mn_cdiv(HW, 64);
     if (blocks < 1) blocks = 1;
@@ -251,14 +255,33 @@ extern "C" int mn_groupnorm_swish(const float* x, int x_cs, float* y, int y_cs, 
     blocks = mn_cdiv(HW, ppb);
     gn_stats_kernel<<<dim3(blocks, N), 256, 0, st>>>(x, x_cs, H, W, C, cpg, valid_w, stats_ws, ppb);
     MN_LAUNCH_CHECK();
-    float2* mr = reinterpret_cast<float2*>(stats_ws + 2 * (size_t)N * G);      // second half of the workspace
-    gn_finalize_kernel<<<mn_cdiv(N * G, 128), 128, 0, st>>>(stats_ws, mr, N, G, H, W, cpg, eps, valid_w);
-    MN_LAUNCH_CHECK();
-    const int64_t total = (int64_t)N * H * W * (C >> 2);
-    MN_REQUIRE(total < (1ll << 31), "tensor too large for 32-bit indexing");
-    gn_apply_kernel<<<(unsigned)mn_cdiv64(total, 256), 256, 0, st>>>(x, x_cs, y, y_cs, gamma, beta, N, H, W, C, cpg, eps, swish, valid_w, mr);
+    gn_finalize_kernel<<<mn_cdiv(N * G, 128), 128, 0, st>>>(stats_ws, reinterpret_cast<float2*>(mean_rstd), N, G, H, W, cpg, eps, valid_w);
     MN_LAUNCH_CHECK();
     return MN_OK;
+}
+
+extern "C" int mn_groupnorm_apply(const float* x, int x_cs, float* y, int y_cs, const float* gamma, const float* beta,
+                                  const float* mean_rstd, int N, int H, int W, int C, int cpg, int swish,
+                                  const int32_t* valid_w, void* stream) {
+    int rc = gn_check(x, x_cs, N, H, W, C, cpg);
+    if (rc != MN_OK) return rc;
+    MN_REQUIRE(y && gamma && beta && mean_rstd && (y_cs & 3) == 0 && ((uintptr_t)y & 15) == 0, "mn_groupnorm_apply: bad args");
+    const int64_t total = (int64_t)N * H * W * (C >> 2);
+    MN_REQUIRE(total < (1ll << 31), "tensor too large for 32-bit indexing");
+    gn_apply_kernel<<<(unsigned)mn_cdiv64(total, 256), 256, 0, (cudaStream_t)stream>>>(x, x_cs, y, y_cs, gamma, beta, N, H, W, C, cpg, 0.f, swish, valid_w,
+                                                                                    reinterpret_cast<const float2*>(mean_rstd));
+    MN_LAUNCH_CHECK();
+    return MN_OK;
+}
+
+extern "C" int mn_groupnorm_swish(const float* x, int x_cs, float* y, int y_cs, const float* gamma, const float* beta,
+                                  int N, int H, int W, int C, int cpg, float eps, int swish,
+                                  const int32_t* valid_w, double* stats_ws, void* stream) {
+    MN_REQUIRE(stats_ws != nullptr, "mn_groupnorm_swish: null workspace");
+    float* mr = reinterpret_cast<float*>(stats_ws + 2 * (size_t)N * (C / (cpg > 0 ? cpg : 1)));   // second part of the workspace
+    int rc = mn_groupnorm_stats(x, x_cs, N, H, W, C, cpg, eps, valid_w, stats_ws, mr, stream);
+    if (rc != MN_OK) return rc;
+    return mn_groupnorm_apply(x, x_cs, y, y_cs, gamma, beta, mr, N, H, W, C, cpg, swish, valid_w, stream);
 }
 
 extern "C" int mn_adain_concat(const float* prior, int prior_cs, const float* feat, int feat_cs, const mn_window* win,

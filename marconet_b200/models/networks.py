@@ -365,11 +365,12 @@ class ResTextBlockV2(nn.Module):
 
 def _res_block(pk, x, valid_w=None):
     """GN -> swish -> conv -> GN -> swish -> conv (+ 1x1 skip), reference networks.py:506-516."""
-    h = ops.groupnorm_swish(x, *pk["n1"], valid_w=valid_w)
-    h = ops.conv2d(h, pk["c1"][0], 3, 3, pad=(1, 1), bias=pk["c1"][1], valid_w=valid_w)
-    h = ops.groupnorm_swish(h, *pk["n2"], valid_w=valid_w)
+    # GroupNorm statistics are a separate (read-only) pass; normalise + swish is fused into the consuming conv's operand stage
+    mr1 = ops.groupnorm_stats(x, valid_w=valid_w)
+    h = ops.conv2d(x, pk["c1"][0], 3, 3, pad=(1, 1), bias=pk["c1"][1], valid_w=valid_w, gn=(mr1,) + tuple(pk["n1"]))
+    mr2 = ops.groupnorm_stats(h, valid_w=valid_w)
     skip = x if pk["co"] is None else ops.conv2d(x, pk["co"][0], 1, 1, bias=pk["co"][1], valid_w=valid_w)
-    return ops.conv2d(h, pk["c2"][0], 3, 3, pad=(1, 1), bias=pk["c2"][1], residual=skip, valid_w=valid_w)
+    return ops.conv2d(h, pk["c2"][0], 3, 3, pad=(1, 1), bias=pk["c2"][1], residual=skip, valid_w=valid_w, gn=(mr2,) + tuple(pk["n2"]))
 
 
 def _two(pk, x, valid_w=None):

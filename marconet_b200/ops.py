@@ -108,8 +108,10 @@ TC_MIN_FLOP = 3.0e7    # tiny launches are latency-bound either way and stay on 
 
 def conv2d(x, w, kh, kw, stride=(1, 1), pad=(0, 0), bias=None, out_scale=None, residual=None,
            res_broadcast=False, act=ACT_NONE, gain=1.0, out=None, out2=None, y2_scale=None,
-           valid_w=None, precision=None, want_y=True, split_k=0):
-    """mn_conv2d_nhwc.  ``w`` is the packed [KH*KW*Cin, Cout] matrix.  Returns y (or (y, y2))."""
+           valid_w=None, precision=None, want_y=True, split_k=0, gn=None):
+    """mn_conv2d_nhwc.  ``w`` is the packed [KH*KW*Cin, Cout] matrix.  Returns y (or (y, y2)).
+    ``gn=(mean_rstd, gamma, beta)``: the conv input is swish(GroupNorm(x)); fused into the tcgen05 v2 kernel's operand-split
+    stage when that kernel runs the layer, otherwise applied by mn_groupnorm_apply first."""
     global LAUNCHES
     lib = _lib.load()
     n, h, wd, cin, x_cs = nhwc_info(x, "x")
@@ -152,19 +154,28 @@ def conv2d(x, w, kh, kw, stride=(1, 1), pad=(0, 0), bias=None, out_scale=None, r
     p.workspace = ws.data_ptr(); p.workspace_bytes = ws.numel() * 4
     p.split_k = split_k
     prec = _DEFAULT_PRECISION if precision is None else precision
+    gn_fused = False
     if prec != PREC_FP32_SIMT:
-        use_tc = (cw is not None and cw.tc_capable() and stride == (1, 1)
-                  and (precision is not None or 2.0 * n * oh * ow * cout * kh * kw * cin >= TC_MIN_FLOP)
-                  and lib.mn_conv2d_tc_supported(ctypes.byref(p)) == 1)
+        ver = 0
+        if (cw is not None and cw.tc_capable() and stride == (1, 1)
+                and (precision is not None or 2.0 * n * oh * ow * cout * kh * kw * cin >= TC_MIN_FLOP)):
+            ver = lib.mn_conv2d_tc_version(ctypes.byref(p))
+        use_tc = ver > 0
         if use_tc:
             hi, lo, sc = cw.tc(prec)
             p.w_tc_hi = hi.data_ptr(); p.w_tc_lo = lo.data_ptr(); p.w_tc_scale = sc.data_ptr()
+            if gn is not None and ver == 2:
+                p.gn_mean_rstd = gn[0].data_ptr(); p.gn_gamma = gn[1].data_ptr(); p.gn_beta = gn[2].data_ptr(); p.gn_swish = 1
+                gn_fused = True
         elif precision is not None:
             raise RuntimeError("conv2d: tensor-core precision requested explicitly but this layer/shape is not supported: "
                                + lib.mn_last_error().decode(errors="replace"))
         else:
             prec = PREC_FP32_SIMT
     p.precision = prec
+    if gn is not None and not gn_fused:      # no fused kernel for this layer: normalise into a temporary first
+        xg = groupnorm_apply(x, gn[0], gn[1], gn[2], valid_w=valid_w)
+        p.x = xg.data_ptr(); p.x_cs = xg.shape[3]
     _lib.check(lib.mn_conv2d_nhwc(ctypes.byref(p), _stream()), "mn_conv2d_nhwc")
     LAUNCHES += 1
     if y2 is not None:
@@ -278,6 +289,30 @@ def groupnorm_swish(x, gamma, beta, cpg=32, eps=1e-6, swish=True, valid_w=None, 
                                               eps, 1 if swish else 0, _ptr(valid_w), _ptr(stats), _stream()),
                "mn_groupnorm_swish")
     LAUNCHES += 3
+    return y
+
+
+def groupnorm_stats(x, cpg=32, eps=1e-6, valid_w=None):
+    """Per (sample, group) mean / rstd [N, C/cpg, 2] of an NHWC view (mn_groupnorm_stats)."""
+    global LAUNCHES
+    n, h, w, c, x_cs = nhwc_info(x, "x")
+    g = c // cpg
+    ws = torch.empty((n * g * 2,), dtype=torch.float64, device=x.device)
+    mr = torch.empty((n, g, 2), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().mn_groupnorm_stats(_ptr(x), x_cs, n, h, w, c, cpg, eps, _ptr(valid_w), _ptr(ws), _ptr(mr), _stream()),
+               "mn_groupnorm_stats")
+    LAUNCHES += 3
+    return mr
+
+
+def groupnorm_apply(x, mr, gamma, beta, cpg=32, swish=True, valid_w=None, out=None):
+    global LAUNCHES
+    n, h, w, c, x_cs = nhwc_info(x, "x")
+    y = out if out is not None else torch.empty((n, h, w, c), dtype=torch.float32, device=x.device)
+    _, _, _, _, y_cs = nhwc_info(y, "out")
+    _lib.check(_lib.load().mn_groupnorm_apply(_ptr(x), x_cs, _ptr(y), y_cs, _ptr(gamma), _ptr(beta), _ptr(mr), n, h, w, c, cpg,
+                                              1 if swish else 0, _ptr(valid_w), _stream()), "mn_groupnorm_apply")
+    LAUNCHES += 1
     return y
 
 

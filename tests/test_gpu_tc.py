@@ -97,6 +97,36 @@ def test_conv_tc_epilogue_and_slices():
             assert y[i, :, :, v:].abs().max().item() == 0
 
 
+@pytest.mark.parametrize("ragged", [False, True])
+def test_conv_tc_fused_groupnorm_swish(ragged):
+    """swish(GroupNorm(x)) built inside the conv's operand-split stage == the standalone GroupNorm kernel + conv."""
+    from marconet_b200 import ops
+    d = _dev()
+    n, h, w, cin, cout = 3, 32, 32, 128, 128
+    x = _rand(n, cin, h, w, seed=20) * 2 + 0.3
+    valid = [32, 17, 5] if ragged else None
+    if ragged:
+        for i, v in enumerate(valid):
+            x[i, :, :, v:] = 0
+    wt = _rand(cout, cin, 3, 3, seed=21, scale=0.04)
+    gamma, beta, bias = _rand(cin, seed=22) * 0.3 + 1, _rand(cin, seed=23) * 0.2, _rand(cout, seed=24)
+    vw = torch.tensor(valid, dtype=torch.int32, device=d) if ragged else None
+    xn = _nhwc(x)
+    mr = ops.groupnorm_stats(xn, valid_w=vw)
+    y = ops.conv2d(xn, _cw(wt), 3, 3, pad=(1, 1), bias=bias.to(d), valid_w=vw, gn=(mr, gamma.to(d), beta.to(d)), precision=ops.PREC_F16X3_TC)
+    y = _nchw(y)
+    for i in range(n):
+        v = valid[i] if ragged else w
+        xi = x[i:i + 1, :, :, :v].double()
+        g = F.group_norm(xi, cin // 32, gamma.double(), beta.double(), eps=1e-6)
+        g = g * torch.sigmoid(g)
+        ref = F.conv2d(g, wt.double(), bias.double(), padding=1).float()
+        err = (y[i:i + 1, :, :, :v] - ref).abs().max().item()
+        assert err <= 3e-5 * max(1.0, ref.abs().max().item()), f"sample {i}: {err}"
+        if v < w:
+            assert y[i, :, :, v:].abs().max().item() == 0
+
+
 def test_tc_unsupported_shape_is_reported():
     from marconet_b200 import ops
     x = _rand(1, 64, 5, 7, seed=9)
