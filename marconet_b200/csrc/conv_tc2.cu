@@ -305,7 +305,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                                 for (int e = 0; e < 4; ++e) {
                                     float u = (tt[e] - mean) * rstd * gg[e] + bb[e];
-                                    if (g.gn_swish) u = u * (1.f / (1.f + expf(-u)));
+                                    if (g.gn_swish) u = u * __frcp_rn(1.f + __expf(-u));     // ex2.approx + rcp: ~1e-7 relative on the sigmoid
                                     tt[e] = inside ? u : 0.f;
                                 }
                                 v = make_float4(tt[0], tt[1], tt[2], tt[3]);

@@ -164,7 +164,8 @@ def conv2d(x, w, kh, kw, stride=(1, 1), pad=(0, 0), bias=None, out_scale=None, r
         if use_tc:
             hi, lo, sc = cw.tc(prec)
             p.w_tc_hi = hi.data_ptr(); p.w_tc_lo = lo.data_ptr(); p.w_tc_scale = sc.data_ptr()
-            if gn is not None and ver == 2:
+            # fuse only where a halo element feeds enough MMA work to hide the exp/normalise cost in the split warps
+            if gn is not None and ver == 2 and cin >= 128 and cout >= 128:
                 p.gn_mean_rstd = gn[0].data_ptr(); p.gn_gamma = gn[1].data_ptr(); p.gn_beta = gn[2].data_ptr(); p.gn_swish = 1
                 gn_fused = True
         elif precision is not None:
