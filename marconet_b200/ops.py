@@ -103,15 +103,18 @@ class ConvWeight:
         return got
 
 
+FUSE_GN = _os.environ.get("MN_FUSE_GN", "0") == "1"
 TC_MIN_FLOP = 3.0e7    # tiny launches are latency-bound either way and stay on the exact fp32 path
 
 
 def conv2d(x, w, kh, kw, stride=(1, 1), pad=(0, 0), bias=None, out_scale=None, residual=None,
            res_broadcast=False, act=ACT_NONE, gain=1.0, out=None, out2=None, y2_scale=None,
-           valid_w=None, precision=None, want_y=True, split_k=0, gn=None):
+           valid_w=None, precision=None, want_y=True, split_k=0, gn=None, gn_fuse=None):
     """mn_conv2d_nhwc.  ``w`` is the packed [KH*KW*Cin, Cout] matrix.  Returns y (or (y, y2)).
     ``gn=(mean_rstd, gamma, beta)``: the conv input is swish(GroupNorm(x)); fused into the tcgen05 v2 kernel's operand-split
-    stage when that kernel runs the layer, otherwise applied by mn_groupnorm_apply first."""
+    stage when ``gn_fuse`` is true and that kernel runs the layer, otherwise applied by mn_groupnorm_apply first.
+    (Measured on B200: with 4 split warps per CTA the fused transform makes the split stage the bottleneck -- 11.6 vs
+    10.1 ms per line -- so the default policy FUSE_GN is off; the kernel path stays tested for a wider split stage.)"""
     global LAUNCHES
     lib = _lib.load()
     n, h, wd, cin, x_cs = nhwc_info(x, "x")
@@ -164,8 +167,7 @@ def conv2d(x, w, kh, kw, stride=(1, 1), pad=(0, 0), bias=None, out_scale=None, r
         if use_tc:
             hi, lo, sc = cw.tc(prec)
             p.w_tc_hi = hi.data_ptr(); p.w_tc_lo = lo.data_ptr(); p.w_tc_scale = sc.data_ptr()
-            # fuse only where a halo element feeds enough MMA work to hide the exp/normalise cost in the split warps
-            if gn is not None and ver == 2 and cin >= 128 and cout >= 128:
+            if gn is not None and ver == 2 and (FUSE_GN if gn_fuse is None else gn_fuse):
                 p.gn_mean_rstd = gn[0].data_ptr(); p.gn_gamma = gn[1].data_ptr(); p.gn_beta = gn[2].data_ptr(); p.gn_swish = 1
                 gn_fused = True
         elif precision is not None:

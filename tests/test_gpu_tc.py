@@ -113,7 +113,8 @@ def test_conv_tc_fused_groupnorm_swish(ragged):
     vw = torch.tensor(valid, dtype=torch.int32, device=d) if ragged else None
     xn = _nhwc(x)
     mr = ops.groupnorm_stats(xn, valid_w=vw)
-    y = ops.conv2d(xn, _cw(wt), 3, 3, pad=(1, 1), bias=bias.to(d), valid_w=vw, gn=(mr, gamma.to(d), beta.to(d)), precision=ops.PREC_F16X3_TC)
+    y = ops.conv2d(xn, _cw(wt), 3, 3, pad=(1, 1), bias=bias.to(d), valid_w=vw, gn=(mr, gamma.to(d), beta.to(d)), gn_fuse=True,
+                   precision=ops.PREC_F16X3_TC)
     y = _nchw(y)
     for i in range(n):
         v = valid[i] if ragged else w
