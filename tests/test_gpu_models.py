@@ -150,3 +150,23 @@ def test_no_priors_and_shapes(gpu_models):
     sr = gpu_models["sr"](lq, [torch.zeros(0, 256, 64, 64, device=dev)], [torch.zeros(0, 512, 32, 32, device=dev)],
                           torch.zeros(1, 0, device=dev))
     assert tuple(sr.shape) == (1, 3, 128, 2048) and torch.isfinite(sr).all()
+
+
+def test_style_interpolation_flow_like_test_w(gpu_models, checkpoints):
+    """The reference's test_w.py:95-108 data flow: two encoder passes, labels = CTC-deduplicated argmax of image 1,
+    priors generated for w = w1*t + w2*(1-t)."""
+    from oracle import restate, synth
+    dev = torch.device("cuda:0")
+    lq1, lq2 = synth.make_lq(1, 21), synth.make_lq(1, 22)
+    logits1, _, w1 = gpu_models["encoder"](lq1.to(dev))
+    _, _, w2 = gpu_models["encoder"](lq2.to(dev))
+    ol1, _, ow1 = restate.encoder_forward(checkpoints["encoder"], lq1)
+    _, _, ow2 = restate.encoder_forward(checkpoints["encoder"], lq2)
+    labels = restate.clear_labels(logits1[0].cpu())
+    assert labels == restate.clear_labels(ol1[0]), "argmax / dedup labels must be bit-exact"
+    labels = torch.tensor(labels[:4], dtype=torch.long).unsqueeze(1)      # first 4 characters keep the CPU oracle quick
+    for t in (0.0, 0.3, 1.0):
+        new_w = w1 * t + w2 * (1 - t)
+        img, _, _ = gpu_models["tspgan"](styles=new_w.repeat(labels.size(0), 1), labels=labels, noise=None)
+        oimg, _, _ = restate.tspgan_forward(checkpoints["tspgan"], (ow1 * t + ow2 * (1 - t)).repeat(labels.size(0), 1), labels)
+        assert _maxerr(img, oimg) <= _tol_internal() * 2
