@@ -40,6 +40,9 @@ def _worker(rank, world, port, n_chars, ok):
         full = _fake_generator(styles, labels, None)
         got = generate_priors_sharded(_fake_generator, styles, labels)
         good = all(torch.equal(a, b) for a, b in zip(full, got))
+        if n_chars % 4 == 0:   # pipelined variant: 2 sub-chunks per rank, async all-gathers
+            got2 = generate_priors_sharded(_fake_generator, styles, labels, pipeline_chunks=2)
+            good &= all(torch.equal(a, b) for a, b in zip(full, got2))
         good &= all(a.permute(0, 2, 3, 1).is_contiguous() for a in got)
         lines = list(shard_lines(5))
         good &= lines == ([0, 1, 2] if rank == 0 else [3, 4])

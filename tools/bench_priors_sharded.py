@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--chars", type=int, default=1024)
     ap.add_argument("--chunk", type=int, default=128, help="characters per generate_priors_sharded call (global)")
     ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--pipeline", type=int, default=1, help="sub-chunks per shard whose all-gather overlaps the next sub-chunk")
     args = ap.parse_args()
     from marconet_b200.models import networks
     from marconet_b200.parallel import generate_priors_sharded
@@ -47,7 +48,7 @@ def main():
         for c0 in range(0, args.chars, args.chunk):
             s, l = styles[c0:c0 + args.chunk], labels[c0:c0 + args.chunk]
             if gather:
-                outs.append(generate_priors_sharded(gen, s, l))
+                outs.append(generate_priors_sharded(gen, s, l, pipeline_chunks=args.pipeline))
             else:
                 from marconet_b200.parallel import shard_range
                 b, e = shard_range(s.shape[0], rank, world)
@@ -74,13 +75,13 @@ def main():
     with torch.no_grad():
         # correctness: gathered == unsharded on the first chunk
         full = gen(styles[:args.chunk], labels[:args.chunk], None)
-        got = generate_priors_sharded(gen, styles[:args.chunk], labels[:args.chunk])
+        got = generate_priors_sharded(gen, styles[:args.chunk], labels[:args.chunk], pipeline_chunks=args.pipeline)
         err = max((a - b).abs().max().item() for a, b in zip(full, got))
         ms_nogather = timed(False)
         ms_gather = timed(True)
     if rank == 0:
         print(json.dumps({
-            "metric": "prior_chars_per_sec", "n_gpus": world, "chars": args.chars, "chunk": args.chunk,
+            "metric": "prior_chars_per_sec", "n_gpus": world, "chars": args.chars, "chunk": args.chunk, "pipeline_chunks": args.pipeline,
             "ms_no_gather": ms_nogather, "chars_per_s_no_gather": args.chars / ms_nogather * 1e3,
             "ms_with_allgather": ms_gather, "chars_per_s_with_allgather": args.chars / ms_gather * 1e3,
             "allgather_bytes_per_rank": int(args.chars * (256 * 64 * 64 + 512 * 32 * 32 + 3 * 128 * 128) * 4),
