@@ -47,8 +47,10 @@ def generate_priors_sharded(generator, styles, labels, group=None, pipeline_chun
     tensors are returned in the generator's own memory format (channels_last views stay channels_last).
 
     pipeline_chunks > 1 (equal shards only): the local shard is generated in that many sub-chunks and the NCCL all-gather of
-    sub-chunk i runs asynchronously while sub-chunk i+1 is generated, hiding the exchange (6 MiB per character, ~0.75 TB/s
-    over NVLink) behind the compute."""
+    sub-chunk i runs asynchronously while sub-chunk i+1 is generated (6 MiB per character, ~0.75 TB/s over NVLink).
+    Measured on 8 x B200 (profiles/r1_priors_sharded_8gpu*.json): no gain (29.0 vs 27.8 ms for 1024 characters) -- the conv
+    kernels are persistent with one CTA per SM, so NCCL's copy kernels get no SM until a conv kernel retires.  Hiding the
+    exchange needs copy-engine / peer-store transfers (symmetric memory), which is next-round work; default stays 1."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     n = labels.shape[0]
