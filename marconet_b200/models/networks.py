@@ -50,6 +50,10 @@ class _PackedModule(nn.Module):
         return super()._apply(fn, *a, **k)
 
     def _get_packed(self, device):
+        first = next(self.parameters())
+        if first.device != device:
+            raise RuntimeError(f"marconet_b200: module parameters live on {first.device} but the input is on {device}; "
+                               f"call .to(device) first (test_sr.py:66-68 does)")
         key = (device, tuple(p._version for p in self.parameters()))
         if self._packed is None or self._packed_key != key:
             with torch.no_grad():
