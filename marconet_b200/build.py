@@ -9,11 +9,9 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmarconet_b200.so")
 STAMP = os.path.join(HERE, "build", "sources.sha256")
 
-NVCC_FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "--use_fast_math=false" if False else "-DMN_BUILD",
-    "-Xptxas", "-v" if os.environ.get("MN_PTXAS_V") else "-O3",
-]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-DMN_BUILD"]
+if os.environ.get("MN_PTXAS_V"):
+    NVCC_FLAGS += ["-Xptxas", "-v"]
 
 
 def _sources():
@@ -59,7 +57,8 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed building libmarconet_b200.so")
-    subprocess.check_call([nvcc_path(), "-shared", "-o", LIB, *objs, "-lcudart_static", "-lrt", "-lpthread", "-ldl"])
+    subprocess.check_call([nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs,
+                           "-lcudart_static", "-lrt", "-lpthread", "-ldl"])
     with open(STAMP, "w") as f:
         f.write(dig)
     return LIB
