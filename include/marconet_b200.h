@@ -54,6 +54,9 @@ typedef enum {
 
 const char* mn_last_error(void);
 int mn_version(void);
+/* Cap the number of CTAs the persistent tensor-core kernels launch (0 = one per SM).  Leaving a few SMs free lets NCCL's
+ * copy kernels run beside them, so an asynchronous all-gather overlaps the next chunk of compute.  Returns the old value. */
+int mn_set_max_ctas(int n);
 /* 1 when the current device is compute capability 10.x (tcgen05/TMA paths usable). */
 int mn_device_is_sm100(void);
 

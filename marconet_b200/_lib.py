@@ -49,6 +49,7 @@ SYMBOLS = {
     "mn_last_error": (c_char_p, []),
     "mn_version": (c_int, []),
     "mn_device_is_sm100": (c_int, []),
+    "mn_set_max_ctas": (c_int, [c_int]),
     "mn_conv2d_nhwc": (c_int, [POINTER(ConvParams), c_void_p]),
     "mn_conv2d_workspace_bytes": (c_int64, [POINTER(ConvParams)]),
     "mn_conv2d_tc_supported": (c_int, [POINTER(ConvParams)]),

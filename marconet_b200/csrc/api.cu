@@ -24,6 +24,14 @@ int mn_num_sms() {
     return sms[dev];
 }
 
+static int g_max_ctas = 0;
+int mn_max_ctas() { return g_max_ctas; }
+extern "C" int mn_set_max_ctas(int n) {
+    const int old = g_max_ctas;
+    g_max_ctas = n > 0 ? n : 0;
+    return old;
+}
+
 extern "C" const char* mn_last_error(void) { return g_err; }
 extern "C" int mn_version(void) { return 100; }
 extern "C" int mn_device_is_sm100(void) {

@@ -513,7 +513,10 @@ int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mbh, const CUtensorMap&
     }
     const Tc2Geom& t = p.t;
     const int total_work = t.m_groups * t.n_tiles;
-    int clusters = mn_num_sms() / t.cs;
+    int sms = mn_num_sms();
+    if (mn_max_ctas() > 0 && mn_max_ctas() < sms) sms = mn_max_ctas();
+    int clusters = sms / t.cs;
+    if (clusters < 1) clusters = 1;
     if (clusters > total_work) clusters = total_work;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(clusters * t.cs, 1, 1);

@@ -58,3 +58,4 @@ __device__ __forceinline__ float mn_warp_max(float v) {
 }
 
 int mn_num_sms();
+int mn_max_ctas();   // 0 = use every SM; >0 = cap for persistent kernels (leaves SMs to concurrent NCCL kernels)

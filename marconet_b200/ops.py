@@ -26,6 +26,11 @@ def set_default_precision(p):
     _DEFAULT_PRECISION = int(p)
 
 
+def set_max_ctas(n):
+    """Cap the persistent conv kernels at n CTAs (0 = all SMs); returns the previous cap."""
+    return _lib.load().mn_set_max_ctas(int(n))
+
+
 def default_precision():
     return _DEFAULT_PRECISION
 

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=128, help="characters per generate_priors_sharded call (global)")
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--pipeline", type=int, default=1, help="sub-chunks per shard whose all-gather overlaps the next sub-chunk")
+    ap.add_argument("--reserve-sms", type=int, default=0, help="SMs left free for NCCL while the conv kernels run")
     args = ap.parse_args()
     from marconet_b200.models import networks
     from marconet_b200.parallel import generate_priors_sharded
@@ -36,6 +37,9 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    if args.reserve_sms > 0:
+        from marconet_b200 import ops
+        ops.set_max_ctas(torch.cuda.get_device_properties(local).multi_processor_count - args.reserve_sms)
     gen = networks.TSPGAN()
     gen.load_state_dict(synth.make_checkpoints(0)["tspgan"], strict=True)
     gen = gen.eval().to(dev)
@@ -81,7 +85,7 @@ def main():
         ms_gather = timed(True)
     if rank == 0:
         print(json.dumps({
-            "metric": "prior_chars_per_sec", "n_gpus": world, "chars": args.chars, "chunk": args.chunk, "pipeline_chunks": args.pipeline,
+            "metric": "prior_chars_per_sec", "n_gpus": world, "chars": args.chars, "chunk": args.chunk, "pipeline_chunks": args.pipeline, "reserve_sms": args.reserve_sms,
             "ms_no_gather": ms_nogather, "chars_per_s_no_gather": args.chars / ms_nogather * 1e3,
             "ms_with_allgather": ms_gather, "chars_per_s_with_allgather": args.chars / ms_gather * 1e3,
             "allgather_bytes_per_rank": int(args.chars * (256 * 64 * 64 + 512 * 32 * 32 + 3 * 128 * 128) * 4),
