@@ -75,29 +75,21 @@ def generate_priors_sharded(generator, styles, labels, group=None, pipeline_chun
 
 
 def _generate_pipelined(generator, styles, labels, group, world, rank, chunks):
-    import torch.cuda as cuda
+    """Block-cyclic sharding: sub-chunk c covers the characters [c*world*sub, (c+1)*world*sub) and rank r generates the
+    r-th block of `sub` of them, so every sub-chunk's all-gather output is one contiguous slice of the final tensors (no
+    re-ordering copy) and its NCCL transfer can overlap the generation of sub-chunk c+1."""
     n = labels.shape[0]
-    per_rank = n // world
-    sub = per_rank // chunks
-    b0 = rank * per_rank
-    gathered, works, keep = None, [], []
+    sub = n // (world * chunks)
+    full, works = None, []
     for c in range(chunks):
-        b = b0 + c * sub
+        b = c * world * sub + rank * sub
         outs = generator(styles[b:b + sub], labels[b:b + sub], None)
-        if gathered is None:   # [world, chunks, sub, H, W, C] buffers, NHWC storage
-            gathered = [torch.empty((world, chunks, sub) + tuple(o.permute(0, 2, 3, 1).shape[1:]), dtype=o.dtype, device=o.device)
-                        for o in outs]
-        for o, buf in zip(outs, gathered):
+        if full is None:
+            full = [torch.empty((n,) + tuple(o.permute(0, 2, 3, 1).shape[1:]), dtype=o.dtype, device=o.device) for o in outs]
+        for o, buf in zip(outs, full):
             local = o.permute(0, 2, 3, 1).contiguous()
-            keep.append(local)
-            # all ranks' sub-chunk c: written to buf[:, c]; a strided destination is not allowed, so gather into a temp
-            tmp = torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-            works.append((dist.all_gather_into_tensor(tmp, local, group=group, async_op=True), tmp, buf, c))
-    for w, tmp, buf, c in works:
+            dst = buf[c * world * sub:(c + 1) * world * sub]
+            works.append((dist.all_gather_into_tensor(dst, local, group=group, async_op=True), local))
+    for w, _ in works:
         w.wait()
-        buf[:, c].copy_(tmp.view((world, -1) + tuple(tmp.shape[1:])))
-    result = []
-    for buf in gathered:
-        full = buf.reshape((world * chunks * sub,) + tuple(buf.shape[3:]))      # rank-major, chunk, sub == global character order
-        result.append(full.permute(0, 3, 1, 2))
-    return tuple(result)
+    return tuple(buf.permute(0, 3, 1, 2) for buf in full)
