@@ -53,7 +53,7 @@ struct Tc2Geom {
     int prec;
 };
 
-template <int NT>
+template <int NT, bool GN>
 __global__ void __launch_bounds__(NUM_THREADS2, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
                 const __grid_constant__ CUtensorMap tmBlo, const ConvGeom g, const Tc2Geom t) {
@@ -257,7 +257,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int epi_after_cb = t.cblocks > 1 ? 1 : 0;
         int prev_work = -1;
         uint32_t hs = 0, hph = 0;
-        const bool gn = g.gn_mr != nullptr;
+        constexpr bool gn = GN;       // fused GroupNorm(+swish) input transform: separate instantiation, zero cost when off
         const int G = g.Cin >> 5;
         for (int work = cluster_id; work < total_work; work += num_clusters) {
             int hn0 = 0, hoy0 = 0, hox0 = 0;
@@ -504,11 +504,11 @@ Tc2Plan plan_tc2(const ConvGeom& g) {
     return p;
 }
 
-template <int NT>
+template <int NT, bool GN>
 int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mbh, const CUtensorMap& mbl, const ConvGeom& g, const Tc2Plan& p, cudaStream_t st) {
     static int smem_set = 0;
     if (smem_set < p.smem) {
-        MN_CUDA_CHECK(cudaFuncSetAttribute(conv_tc2_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        MN_CUDA_CHECK(cudaFuncSetAttribute(conv_tc2_kernel<NT, GN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         smem_set = SMEM_LIMIT;
     }
     const Tc2Geom& t = p.t;
@@ -527,7 +527,7 @@ int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mbh, const CUtensorMap&
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = t.cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    MN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<NT>, ma, mbh, mbl, g, t));
+    MN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<NT, GN>, ma, mbh, mbl, g, t));
     return MN_OK;
 }
 
@@ -570,5 +570,6 @@ int mn_conv_tc2_launch(const ConvGeom& g, const void* w_hi, const void* w_lo, co
     }
     t.wscale = w_scale + 1;
     t.prec = prec;
-    return p.NT == 128 ? launch_tc2<128>(ma, mbh, mbl, g, p, st) : launch_tc2<64>(ma, mbh, mbl, g, p, st);
+    if (g.gn_mr) return p.NT == 128 ? launch_tc2<128, true>(ma, mbh, mbl, g, p, st) : launch_tc2<64, true>(ma, mbh, mbl, g, p, st);
+    return p.NT == 128 ? launch_tc2<128, false>(ma, mbh, mbl, g, p, st) : launch_tc2<64, false>(ma, mbh, mbl, g, p, st);
 }
