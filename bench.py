@@ -99,7 +99,7 @@ class ClockSampler(threading.Thread):
 
 
 def make_inputs(lines, chars, seed):
-    from oracle import synth   # seeded synthetic input generators only (no oracle compute on this leg)
+    from marconet_b200.testing import synth   # seeded synthetic input generators (random tensors only)
     lq = synth.make_lq(lines, seed)
     labels = [synth.make_labels(chars, seed + b) for b in range(lines)]
     locs = synth.make_locs(lines, chars)
@@ -191,7 +191,7 @@ def run_ours(args):
     import torch.distributed as dist
     from marconet_b200 import _lib, ops
     from marconet_b200.models import networks
-    from oracle import synth   # synthetic checkpoint generator (weights only)
+    from marconet_b200.testing import synth   # synthetic checkpoint generator (random weights only)
 
     _lib.load()   # fail loudly if the CUDA library is missing
     world = int(os.environ.get("WORLD_SIZE", "1"))

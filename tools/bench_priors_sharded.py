@@ -28,7 +28,7 @@ def main():
     args = ap.parse_args()
     from marconet_b200.models import networks
     from marconet_b200.parallel import generate_priors_sharded
-    from oracle import synth
+    from marconet_b200.testing import synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
