@@ -106,6 +106,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (cs > 1) cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) may overlap the
+    // tail of the previous kernel in the stream; from here on we read its results, so wait for it to complete and flush.
+    // Let our own dependents start their prologue as soon as SMs free up.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     auto tile_origin = [&](int work, int& n0, int& oy0, int& ox0) {
         int m_tile = (work / t.n_tiles) * cs + (int)crank;
@@ -523,10 +528,14 @@ int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mbh, const CUtensorMap&
     cfg.blockDim = dim3(NUM_THREADS2, 1, 1);
     cfg.dynamicSmemBytes = p.smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = t.cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    static int pdl = -1;
+    if (pdl < 0) { const char* e = getenv("MN_TC_PDL"); pdl = (e && e[0] == '0') ? 0 : 1; }
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 2 : 1;
     MN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<NT, GN>, ma, mbh, mbl, g, t));
     return MN_OK;
 }
