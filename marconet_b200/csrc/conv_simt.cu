@@ -17,6 +17,7 @@ constexpr int NTHREADS = 256;
 
 template <int BN, bool VEC_A, bool VEC_B>
 __global__ void __launch_bounds__(NTHREADS, 2) conv_igemm_f32_kernel(const ConvGeom g) {
+    mn_pdl_prologue();
     constexpr int TN = BN / 16;       // columns per thread (8 or 4)
     constexpr int NS = TN / 4;        // float4 strips per thread along N
     __shared__ __align__(16) float As[2][BK][BM];
@@ -172,6 +173,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_igemm_f32_kernel(const ConvG
 }
 
 __global__ void conv_splitk_reduce_kernel(const ConvGeom g) {
+    mn_pdl_prologue();
     const int ngroups = (g.Cout + 3) >> 2;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)g.M * ngroups) return;
@@ -188,10 +190,10 @@ __global__ void conv_splitk_reduce_kernel(const ConvGeom g) {
 template <int BN>
 int launch_simt(const ConvGeom& g, bool vec_a, bool vec_b, cudaStream_t st) {
     dim3 grid(mn_cdiv(g.M, BM), mn_cdiv(g.Cout, BN), g.splits);
-    if (vec_a && vec_b) conv_igemm_f32_kernel<BN, true, true><<<grid, NTHREADS, 0, st>>>(g);
-    else if (vec_a) conv_igemm_f32_kernel<BN, true, false><<<grid, NTHREADS, 0, st>>>(g);
-    else if (vec_b) conv_igemm_f32_kernel<BN, false, true><<<grid, NTHREADS, 0, st>>>(g);
-    else conv_igemm_f32_kernel<BN, false, false><<<grid, NTHREADS, 0, st>>>(g);
+    if (vec_a && vec_b) MN_CUDA_CHECK((mn_launch(conv_igemm_f32_kernel<BN, true, true>, dim3(grid), dim3(NTHREADS), 0, st, g)));
+    else if (vec_a) MN_CUDA_CHECK((mn_launch(conv_igemm_f32_kernel<BN, true, false>, dim3(grid), dim3(NTHREADS), 0, st, g)));
+    else if (vec_b) MN_CUDA_CHECK((mn_launch(conv_igemm_f32_kernel<BN, false, true>, dim3(grid), dim3(NTHREADS), 0, st, g)));
+    else MN_CUDA_CHECK((mn_launch(conv_igemm_f32_kernel<BN, false, false>, dim3(grid), dim3(NTHREADS), 0, st, g)));
     MN_LAUNCH_CHECK();
     return MN_OK;
 }
@@ -233,7 +235,7 @@ int mn_conv_simt_launch(ConvGeom g, const float* x_ptr_for_align, cudaStream_t s
     if (rc != MN_OK) return rc;
     if (g.splits > 1) {
         const int64_t total = (int64_t)g.M * ((g.Cout + 3) / 4);
-        conv_splitk_reduce_kernel<<<(unsigned)mn_cdiv64(total, 256), 256, 0, st>>>(g);
+        MN_CUDA_CHECK((mn_launch(conv_splitk_reduce_kernel, dim3((unsigned)mn_cdiv64(total, 256)), dim3(256), 0, st, g)));
         MN_LAUNCH_CHECK();
     }
     return MN_OK;

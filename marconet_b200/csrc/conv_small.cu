@@ -12,6 +12,7 @@ constexpr int PIX_PITCH = CCH + 4;            // floats per halo pixel (padding 
 
 template <int COUT>
 __global__ void __launch_bounds__(PH * PW) conv3x3_small_cout_kernel(const ConvGeom g) {
+    mn_pdl_prologue();
     __shared__ __align__(16) float halo[(PH + 2) * (PW + 2) * PIX_PITCH];
     __shared__ __align__(16) float wsm[9 * CCH * 4];       // [tap][c][4] (COUT padded to 4)
     const int tx = threadIdx.x % PW, ty = threadIdx.x / PW;
@@ -77,10 +78,10 @@ bool mn_conv_small_supported(const ConvGeom& g) {
 int mn_conv_small_launch(const ConvGeom& g, cudaStream_t st) {
     const int blocks = g.N * ((g.H + PH - 1) / PH) * ((g.W + PW - 1) / PW);
     switch (g.Cout) {
-        case 1: conv3x3_small_cout_kernel<1><<<blocks, PH * PW, 0, st>>>(g); break;
-        case 2: conv3x3_small_cout_kernel<2><<<blocks, PH * PW, 0, st>>>(g); break;
-        case 3: conv3x3_small_cout_kernel<3><<<blocks, PH * PW, 0, st>>>(g); break;
-        default: conv3x3_small_cout_kernel<4><<<blocks, PH * PW, 0, st>>>(g); break;
+        case 1: MN_CUDA_CHECK((mn_launch(conv3x3_small_cout_kernel<1>, dim3(blocks), dim3(PH * PW), 0, st, g))); break;
+        case 2: MN_CUDA_CHECK((mn_launch(conv3x3_small_cout_kernel<2>, dim3(blocks), dim3(PH * PW), 0, st, g))); break;
+        case 3: MN_CUDA_CHECK((mn_launch(conv3x3_small_cout_kernel<3>, dim3(blocks), dim3(PH * PW), 0, st, g))); break;
+        default: MN_CUDA_CHECK((mn_launch(conv3x3_small_cout_kernel<4>, dim3(blocks), dim3(PH * PW), 0, st, g))); break;
     }
     MN_LAUNCH_CHECK();
     return MN_OK;

@@ -6,6 +6,7 @@ namespace {
 
 // ---------------------------------------------------------------- PixelNorm (networks.py:170-171)
 __global__ void pixelnorm_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int C) {
+    mn_pdl_prologue();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= N) return;
@@ -21,6 +22,7 @@ __global__ void pixelnorm_kernel(const float* __restrict__ x, float* __restrict_
 __global__ void select_text_kernel(const float* __restrict__ emb, const int64_t* __restrict__ labels,
                                    const float* __restrict__ s, int s_stride, float* __restrict__ out,
                                    int N, int L, int C) {
+    mn_pdl_prologue();
     // out: [N, 4, 4*L, C]; one thread per 4 channels of one output pixel
     const int c4 = C >> 2;
     const int64_t total = (int64_t)N * 16 * L * c4;
@@ -44,6 +46,7 @@ __global__ void select_text_kernel(const float* __restrict__ emb, const int64_t*
 // ---------------------------------------------------------------- demodulation (networks.py:284-287)
 __global__ void demod_kernel(const float* __restrict__ s, int s_stride, const float* __restrict__ wsq,
                              float* __restrict__ demod, int N, int Cin, int Cout) {
+    mn_pdl_prologue();
     const int o = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = blockIdx.y;
     if (o >= Cout) return;
@@ -59,6 +62,7 @@ __global__ void demod_kernel(const float* __restrict__ s, int s_stride, const fl
 // All demodulation tables of a generator pass in ONE launch: grid (cout tiles, N, layers), 64 columns x 4 k-slices.
 __global__ void __launch_bounds__(256) demod_batched_kernel(const float* __restrict__ s_all, int s_stride, const mn_demod_desc* __restrict__ descs,
                                                             float* __restrict__ out_all, int out_stride) {
+    mn_pdl_prologue();
     const mn_demod_desc d = descs[blockIdx.z];
     const int col = threadIdx.x & 63, ks = threadIdx.x >> 6;
     const int o = blockIdx.x * 64 + col;
@@ -93,6 +97,7 @@ __device__ __forceinline__ void bilin_coords(int o, int size, int& i0, int& i1, 
 __global__ void resample_modulate_kernel(const float* __restrict__ x, int x_cs, float* __restrict__ y, int y_cs,
                                          const float* __restrict__ s, int s_stride,
                                          int N, int H, int W, int C, int up) {
+    mn_pdl_prologue();
     const int OH = up ? 2 * H : H, OW = up ? 2 * W : W;
     const int c4 = C >> 2;
     const int64_t total = (int64_t)N * OH * OW * c4;
@@ -136,6 +141,7 @@ __global__ void torgb_kernel(const float* __restrict__ x, int x_cs, const float*
                              const float* __restrict__ w, const float* __restrict__ bias,
                              const float* __restrict__ skip, float* __restrict__ out,
                              int N, int H, int W, int C) {
+    mn_pdl_prologue();
     const int n = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -190,7 +196,7 @@ __global__ void torgb_kernel(const float* __restrict__ x, int x_cs, const float*
 
 extern "C" int mn_pixelnorm(const float* x, float* y, int N, int C, void* stream) {
     MN_REQUIRE(x && y && N > 0 && C > 0, "mn_pixelnorm: bad args");
-    pixelnorm_kernel<<<mn_cdiv(N, 4), 128, 0, (cudaStream_t)stream>>>(x, y, N, C);
+    MN_CUDA_CHECK((mn_launch(pixelnorm_kernel, dim3(mn_cdiv(N, 4)), dim3(128), 0, (cudaStream_t)stream, x, y, N, C)));
     MN_LAUNCH_CHECK();
     return MN_OK;
 }
@@ -200,7 +206,7 @@ extern "C" int mn_select_text(const float* emb, const int64_t* labels, const flo
     MN_REQUIRE(emb && labels && out && N > 0 && L > 0 && C > 0 && (C & 3) == 0, "mn_select_text: bad args");
     const int64_t total = (int64_t)N * 16 * L * (C >> 2);
     MN_REQUIRE(total < (1ll << 31), "tensor too large for 32-bit indexing");
-    select_text_kernel<<<(unsigned)mn_cdiv64(total, 256), 256, 0, (cudaStream_t)stream>>>(emb, labels, s, s_stride, out, N, L, C);
+    MN_CUDA_CHECK((mn_launch(select_text_kernel, dim3((unsigned)mn_cdiv64(total, 256)), dim3(256), 0, (cudaStream_t)stream, emb, labels, s, s_stride, out, N, L, C)));
     MN_LAUNCH_CHECK();
     return MN_OK;
 }
@@ -208,7 +214,7 @@ extern "C" int mn_select_text(const float* emb, const int64_t* labels, const flo
 extern "C" int mn_demod(const float* s, int s_stride, const float* wsq, float* demod, int N, int Cin, int Cout, void* stream) {
     MN_REQUIRE(s && wsq && demod && N > 0 && Cin > 0 && Cout > 0, "mn_demod: bad args");
     dim3 grid(mn_cdiv(Cout, 128), N);
-    demod_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(s, s_stride, wsq, demod, N, Cin, Cout);
+    MN_CUDA_CHECK((mn_launch(demod_kernel, dim3(grid), dim3(128), 0, (cudaStream_t)stream, s, s_stride, wsq, demod, N, Cin, Cout)));
     MN_LAUNCH_CHECK();
     return MN_OK;
 }
@@ -221,7 +227,7 @@ extern "C" int mn_resample_modulate(const float* x, int x_cs, float* y, int y_cs
     const int OH = up ? 2 * H : H, OW = up ? 2 * W : W;
     const int64_t total = (int64_t)N * OH * OW * (C >> 2);
     MN_REQUIRE(total < (1ll << 31), "tensor too large for 32-bit indexing");
-    resample_modulate_kernel<<<(unsigned)mn_cdiv64(total, 256), 256, 0, (cudaStream_t)stream>>>(x, x_cs, y, y_cs, s, s_stride, N, H, W, C, up);
+    MN_CUDA_CHECK((mn_launch(resample_modulate_kernel, dim3((unsigned)mn_cdiv64(total, 256)), dim3(256), 0, (cudaStream_t)stream, x, x_cs, y, y_cs, s, s_stride, N, H, W, C, up)));
     MN_LAUNCH_CHECK();
     return MN_OK;
 }
@@ -239,10 +245,10 @@ extern "C" int mn_torgb(const float* x, int x_cs, const float* s, int s_stride, 
     dim3 grid(blocks, N);
     cudaStream_t st = (cudaStream_t)stream;
     switch (C / 32) {
-        case 4: torgb_kernel<4><<<grid, 256, 0, st>>>(x, x_cs, s, s_stride, w, bias, skip, out, N, H, W, C); break;
-        case 8: torgb_kernel<8><<<grid, 256, 0, st>>>(x, x_cs, s, s_stride, w, bias, skip, out, N, H, W, C); break;
-        case 12: torgb_kernel<12><<<grid, 256, 0, st>>>(x, x_cs, s, s_stride, w, bias, skip, out, N, H, W, C); break;
-        case 16: torgb_kernel<16><<<grid, 256, 0, st>>>(x, x_cs, s, s_stride, w, bias, skip, out, N, H, W, C); break;
+        case 4: MN_CUDA_CHECK((mn_launch(torgb_kernel<4>, dim3(grid), dim3(256), 0, st, x, x_cs, s, s_stride, w, bias, skip, out, N, H, W, C))); break;
+        case 8: MN_CUDA_CHECK((mn_launch(torgb_kernel<8>, dim3(grid), dim3(256), 0, st, x, x_cs, s, s_stride, w, bias, skip, out, N, H, W, C))); break;
+        case 12: MN_CUDA_CHECK((mn_launch(torgb_kernel<12>, dim3(grid), dim3(256), 0, st, x, x_cs, s, s_stride, w, bias, skip, out, N, H, W, C))); break;
+        case 16: MN_CUDA_CHECK((mn_launch(torgb_kernel<16>, dim3(grid), dim3(256), 0, st, x, x_cs, s, s_stride, w, bias, skip, out, N, H, W, C))); break;
         default: mn_set_error("mn_torgb: unsupported C=%d", C); return MN_ERR_UNSUPPORTED;
     }
     MN_LAUNCH_CHECK();
@@ -252,7 +258,7 @@ extern "C" int mn_torgb(const float* x, int x_cs, const float* s, int s_stride, 
 extern "C" int mn_demod_batched(const float* s_all, int s_stride, const mn_demod_desc* descs, int n_layers, int max_cout,
                                 float* out_all, int out_stride, int N, void* stream) {
     MN_REQUIRE(s_all && descs && out_all && n_layers > 0 && max_cout > 0 && N > 0, "mn_demod_batched: bad args");
-    demod_batched_kernel<<<dim3(mn_cdiv(max_cout, 64), N, n_layers), 256, 0, (cudaStream_t)stream>>>(s_all, s_stride, descs, out_all, out_stride);
+    MN_CUDA_CHECK((mn_launch(demod_batched_kernel, dim3(dim3(mn_cdiv(max_cout, 64), N, n_layers)), dim3(256), 0, (cudaStream_t)stream, s_all, s_stride, descs, out_all, out_stride)));
     MN_LAUNCH_CHECK();
     return MN_OK;
 }

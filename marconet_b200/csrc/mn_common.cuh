@@ -57,5 +57,23 @@ __device__ __forceinline__ float mn_warp_max(float v) {
     return v;
 }
 
+// Programmatic dependent launch: every kernel of the library starts with griddepcontrol.wait (wait for the previous kernel in
+// the stream to complete and flush -- normal stream semantics) followed by launch_dependents, and is launched with the
+// programmatic-stream-serialization attribute, so launch latency / block scheduling of kernel i+1 overlaps the tail of kernel i.
+__device__ __forceinline__ void mn_pdl_prologue() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t mn_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 int mn_num_sms();
 int mn_max_ctas();   // 0 = use every SM; >0 = cap for persistent kernels (leaves SMs to concurrent NCCL kernels)

@@ -10,6 +10,7 @@ namespace {
 // 32-channel group by shuffles, over the block in shared memory, then one fp64 atomicAdd per (block, group, moment).
 __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ x, int x_cs, int H, int W, int C, int cpg,
                                                        const int32_t* __restrict__ valid_w, double* __restrict__ stats, int pix_per_block) {
+    mn_pdl_prologue();
     const int n = blockIdx.y;
     const int tpp = C >> 2;                        // threads per pixel
     const int ppi = blockDim.x / tpp;              // pixels per iteration (host guarantees >= 1)
@@ -54,6 +55,7 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
 // (sum, sumsq) fp64 -> (mean, rstd) fp32 per (sample, group); biased variance like torch.nn.GroupNorm.
 __global__ void gn_finalize_kernel(const double* __restrict__ stats, float2* __restrict__ mr, int N, int G, int H, int W, int cpg, float eps,
                                    const int32_t* __restrict__ valid_w) {
+    mn_pdl_prologue();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N * G) return;
     const int n = i / G;
@@ -69,6 +71,7 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, int x_cs, float* __
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 int N, int H, int W, int C, int cpg, float eps, int swish,
                                 const int32_t* __restrict__ valid_w, const float2* __restrict__ mr) {
+    mn_pdl_prologue();
     const int c4 = C >> 2;
     const int64_t total = (int64_t)N * H * W * c4;
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;     // host guarantees total < 2^31: 32-bit div/mod only
@@ -104,6 +107,7 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, int x_cs, float* __
 __global__ void __launch_bounds__(256) adain_stats_kernel(const float* __restrict__ prior, int prior_cs, const float* __restrict__ feat, int feat_cs,
                                                           const mn_window* __restrict__ win, double* __restrict__ stats,
                                                           int H, int Wp, int W, int C, int pix_per_block) {
+    mn_pdl_prologue();
     const int i = blockIdx.y;
     const mn_window wn = win[i];
     const int wv = wn.x2 - wn.x1;
@@ -158,6 +162,7 @@ __global__ void __launch_bounds__(256) adain_stats_kernel(const float* __restric
 // fp64 moments -> fp32 {prior mean, prior std, lq mean, lq std} per (character, channel); unbiased variance + 1e-5.
 __global__ void adain_finalize_kernel(const double* __restrict__ stats, const mn_window* __restrict__ win, float4* __restrict__ ms,
                                       int Nc, int C, int H) {
+    mn_pdl_prologue();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= Nc * C) return;
     const mn_window wn = win[idx / C];
@@ -172,6 +177,7 @@ __global__ void adain_finalize_kernel(const double* __restrict__ stats, const mn
 __global__ void adain_apply_kernel(const float* __restrict__ prior, int prior_cs, const float* __restrict__ feat, int feat_cs,
                                    const mn_window* __restrict__ win, const float4* __restrict__ ms, float* __restrict__ out,
                                    int Nc, int H, int Wp, int W, int C) {
+    mn_pdl_prologue();
     const int c4 = C >> 2;
     const int64_t total = (int64_t)Nc * H * Wp * c4;
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;     // host guarantees total < 2^31: 32-bit div/mod only
@@ -205,6 +211,7 @@ __global__ void window_scatter_kernel(const float* __restrict__ feat, int feat_c
                                       const float* __restrict__ shift, const int32_t* __restrict__ owner,
                                       const mn_window* __restrict__ win, float* __restrict__ out, int out_cs,
                                       int B, int H, int W, int Wp, int C) {
+    mn_pdl_prologue();
     const int c4 = C >> 2;
     const int64_t total = (int64_t)B * H * W * c4;
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;     // host guarantees total < 2^31: 32-bit div/mod only
@@ -253,9 +260,9 @@ extern "C" int mn_groupnorm_stats(const float* x, int x_cs, int N, int H, int W,
     if (blocks < 1) blocks = 1;
     const int ppb = mn_cdiv(HW, blocks);
     blocks = mn_cdiv(HW, ppb);
-    gn_stats_kernel<<<dim3(blocks, N), 256, 0, st>>>(x, x_cs, H, W, C, cpg, valid_w, stats_ws, ppb);
+    MN_CUDA_CHECK((mn_launch(gn_stats_kernel, dim3(dim3(blocks, N)), dim3(256), 0, st, x, x_cs, H, W, C, cpg, valid_w, stats_ws, ppb)));
     MN_LAUNCH_CHECK();
-    gn_finalize_kernel<<<mn_cdiv(N * G, 128), 128, 0, st>>>(stats_ws, reinterpret_cast<float2*>(mean_rstd), N, G, H, W, cpg, eps, valid_w);
+    MN_CUDA_CHECK((mn_launch(gn_finalize_kernel, dim3(mn_cdiv(N * G, 128)), dim3(128), 0, st, stats_ws, reinterpret_cast<float2*>(mean_rstd), N, G, H, W, cpg, eps, valid_w)));
     MN_LAUNCH_CHECK();
     return MN_OK;
 }
@@ -268,8 +275,8 @@ extern "C" int mn_groupnorm_apply(const float* x, int x_cs, float* y, int y_cs, 
     MN_REQUIRE(y && gamma && beta && mean_rstd && (y_cs & 3) == 0 && ((uintptr_t)y & 15) == 0, "mn_groupnorm_apply: bad args");
     const int64_t total = (int64_t)N * H * W * (C >> 2);
     MN_REQUIRE(total < (1ll << 31), "tensor too large for 32-bit indexing");
-    gn_apply_kernel<<<(unsigned)mn_cdiv64(total, 256), 256, 0, (cudaStream_t)stream>>>(x, x_cs, y, y_cs, gamma, beta, N, H, W, C, cpg, 0.f, swish, valid_w,
-                                                                                    reinterpret_cast<const float2*>(mean_rstd));
+    MN_CUDA_CHECK((mn_launch(gn_apply_kernel, dim3((unsigned)mn_cdiv64(total, 256)), dim3(256), 0, (cudaStream_t)stream, x, x_cs, y, y_cs, gamma, beta, N, H, W, C, cpg, 0.f, swish, valid_w,
+                                                                                    reinterpret_cast<const float2*>(mean_rstd))));
     MN_LAUNCH_CHECK();
     return MN_OK;
 }
@@ -298,14 +305,14 @@ extern "C" int mn_adain_concat(const float* prior, int prior_cs, const float* fe
     if (blocks < 1) blocks = 1;
     const int ppb = mn_cdiv(npix_max, blocks);
     blocks = mn_cdiv(npix_max, ppb);
-    adain_stats_kernel<<<dim3(blocks, Nc), 256, 0, st>>>(prior, prior_cs, feat, feat_cs, win, stats_ws, H, Wp, W, C, ppb);
+    MN_CUDA_CHECK((mn_launch(adain_stats_kernel, dim3(dim3(blocks, Nc)), dim3(256), 0, st, prior, prior_cs, feat, feat_cs, win, stats_ws, H, Wp, W, C, ppb)));
     MN_LAUNCH_CHECK();
     float4* ms = reinterpret_cast<float4*>(stats_ws + 4 * (size_t)Nc * C);    // second part of the workspace
-    adain_finalize_kernel<<<mn_cdiv(Nc * C, 256), 256, 0, st>>>(stats_ws, win, ms, Nc, C, H);
+    MN_CUDA_CHECK((mn_launch(adain_finalize_kernel, dim3(mn_cdiv(Nc * C, 256)), dim3(256), 0, st, stats_ws, win, ms, Nc, C, H)));
     MN_LAUNCH_CHECK();
     const int64_t total = (int64_t)Nc * H * Wp * (C >> 2);
     MN_REQUIRE(total < (1ll << 31), "tensor too large for 32-bit indexing");
-    adain_apply_kernel<<<(unsigned)mn_cdiv64(total, 256), 256, 0, st>>>(prior, prior_cs, feat, feat_cs, win, ms, out, Nc, H, Wp, W, C);
+    MN_CUDA_CHECK((mn_launch(adain_apply_kernel, dim3((unsigned)mn_cdiv64(total, 256)), dim3(256), 0, st, prior, prior_cs, feat, feat_cs, win, ms, out, Nc, H, Wp, W, C)));
     MN_LAUNCH_CHECK();
     return MN_OK;
 }
@@ -317,7 +324,7 @@ extern "C" int mn_window_scatter(const float* feat, int feat_cs, const float* sc
     MN_REQUIRE(B > 0 && H > 0 && W > 0 && Wp > 0 && (C & 3) == 0 && (feat_cs & 3) == 0 && (out_cs & 3) == 0, "mn_window_scatter: bad dims");
     const int64_t total = (int64_t)B * H * W * (C >> 2);
     MN_REQUIRE(total < (1ll << 31), "tensor too large for 32-bit indexing");
-    window_scatter_kernel<<<(unsigned)mn_cdiv64(total, 256), 256, 0, (cudaStream_t)stream>>>(feat, feat_cs, scale, shift, owner, win, out, out_cs, B, H, W, Wp, C);
+    MN_CUDA_CHECK((mn_launch(window_scatter_kernel, dim3((unsigned)mn_cdiv64(total, 256)), dim3(256), 0, (cudaStream_t)stream, feat, feat_cs, scale, shift, owner, win, out, out_cs, B, H, W, Wp, C)));
     MN_LAUNCH_CHECK();
     return MN_OK;
 }

@@ -6,6 +6,7 @@ namespace {
 
 __global__ void layernorm_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, int rows, int dim, float eps) {
+    mn_pdl_prologue();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -24,6 +25,7 @@ template <int TMAX>
 __global__ void token_mix_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                                  const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out,
                                  int B, int T, int To, int D, float eps) {
+    mn_pdl_prologue();
     const int d = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
     if (d >= D) return;
@@ -49,6 +51,7 @@ __global__ void token_mix_kernel(const float* __restrict__ x, const float* __res
 // One CTA per (batch, head).  S <= 64, dh == 64.
 __global__ void __launch_bounds__(256) attention_kernel(const float* __restrict__ qkv, float* __restrict__ out,
                                                         int S, int heads, float scale) {
+    mn_pdl_prologue();
     constexpr int DH = 64, SM = 64;
     extern __shared__ __align__(16) float att_smem[];
     float (*Q)[DH] = reinterpret_cast<float (*)[DH]>(att_smem);
@@ -104,6 +107,7 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, boo
 __global__ void __launch_bounds__(128) linear_small_m_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                              const float* __restrict__ bias, const float* __restrict__ residual,
                                                              float* __restrict__ y, int M, int K, int N, int act, float gain) {
+    mn_pdl_prologue();
     constexpr int ST = 4;
     __shared__ __align__(16) float Xs[ST][64][36];
     __shared__ __align__(16) float Ws[ST][32][16];
@@ -161,6 +165,7 @@ __global__ void __launch_bounds__(128) linear_small_m_kernel(const float* __rest
 
 // 32x32 smem-tiled transposes between [C][HW] and [HW][C] per sample.
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int HW, int y_cs) {
+    mn_pdl_prologue();
     __shared__ float t[32][33];
     const int n = blockIdx.z;
     const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -175,6 +180,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restri
     }
 }
 __global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, int x_cs, float* __restrict__ y, int C, int HW) {
+    mn_pdl_prologue();
     __shared__ float t[32][33];
     const int n = blockIdx.z;
     const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -194,7 +200,7 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, int x_cs, float
 extern "C" int mn_layernorm(const float* x, float* y, const float* gamma, const float* beta, int rows, int dim,
                             float eps, void* stream) {
     MN_REQUIRE(x && y && gamma && beta && rows > 0 && dim > 0, "mn_layernorm: bad args");
-    layernorm_kernel<<<mn_cdiv(rows, 4), 128, 0, (cudaStream_t)stream>>>(x, y, gamma, beta, rows, dim, eps);
+    MN_CUDA_CHECK((mn_launch(layernorm_kernel, dim3(mn_cdiv(rows, 4)), dim3(128), 0, (cudaStream_t)stream, x, y, gamma, beta, rows, dim, eps)));
     MN_LAUNCH_CHECK();
     return MN_OK;
 }
@@ -203,7 +209,7 @@ extern "C" int mn_linear_small_m(const float* x, const float* w, const float* bi
                                  int M, int K, int N, int act, float gain, void* stream) {
     MN_REQUIRE(x && w && y && M > 0 && M <= 64 && K > 0 && K % 32 == 0 && N > 0 && N % 16 == 0, "mn_linear_small_m: needs M<=64, K%32==0, N%16==0");
     MN_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0, "mn_linear_small_m: x, w must be 16-byte aligned");
-    linear_small_m_kernel<<<N / 16, 128, 0, (cudaStream_t)stream>>>(x, w, bias, residual, y, M, K, N, act, gain);
+    MN_CUDA_CHECK((mn_launch(linear_small_m_kernel, dim3(N / 16), dim3(128), 0, (cudaStream_t)stream, x, w, bias, residual, y, M, K, N, act, gain)));
     MN_LAUNCH_CHECK();
     return MN_OK;
 }
@@ -211,7 +217,7 @@ extern "C" int mn_linear_small_m(const float* x, const float* w, const float* bi
 extern "C" int mn_token_mix(const float* x, const float* gamma, const float* beta, const float* w, const float* bias,
                             float* out, int B, int T, int To, int D, float eps, void* stream) {
     MN_REQUIRE(x && gamma && beta && w && bias && out && B > 0 && T > 0 && T <= 64 && To > 0 && D > 0, "mn_token_mix: bad args (T<=64)");
-    token_mix_kernel<64><<<dim3(mn_cdiv(D, 128), B), 128, 0, (cudaStream_t)stream>>>(x, gamma, beta, w, bias, out, B, T, To, D, eps);
+    MN_CUDA_CHECK((mn_launch(token_mix_kernel<64>, dim3(dim3(mn_cdiv(D, 128), B)), dim3(128), 0, (cudaStream_t)stream, x, gamma, beta, w, bias, out, B, T, To, D, eps)));
     MN_LAUNCH_CHECK();
     return MN_OK;
 }
@@ -225,7 +231,7 @@ extern "C" int mn_attention(const float* qkv, float* out, int B, int S, int head
         MN_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
         attr_set = true;
     }
-    attention_kernel<<<B * heads, 256, kSmem, (cudaStream_t)stream>>>(qkv, out, S, heads, scale);
+    MN_CUDA_CHECK((mn_launch(attention_kernel, dim3(B * heads), dim3(256), kSmem, (cudaStream_t)stream, qkv, out, S, heads, scale)));
     MN_LAUNCH_CHECK();
     return MN_OK;
 }
@@ -233,7 +239,7 @@ extern "C" int mn_attention(const float* qkv, float* out, int B, int S, int head
 extern "C" int mn_nchw_to_nhwc(const float* x, float* y, int N, int C, int H, int W, int y_cs, void* stream) {
     MN_REQUIRE(x && y && N > 0 && C > 0 && H > 0 && W > 0 && y_cs >= C, "mn_nchw_to_nhwc: bad args");
     dim3 grid(mn_cdiv(H * W, 32), mn_cdiv(C, 32), N);
-    nchw_to_nhwc_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(x, y, C, H * W, y_cs);
+    MN_CUDA_CHECK((mn_launch(nchw_to_nhwc_kernel, dim3(grid), dim3(dim3(32, 8)), 0, (cudaStream_t)stream, x, y, C, H * W, y_cs)));
     MN_LAUNCH_CHECK();
     return MN_OK;
 }
@@ -241,7 +247,7 @@ extern "C" int mn_nchw_to_nhwc(const float* x, float* y, int N, int C, int H, in
 extern "C" int mn_nhwc_to_nchw(const float* x, int x_cs, float* y, int N, int C, int H, int W, void* stream) {
     MN_REQUIRE(x && y && N > 0 && C > 0 && H > 0 && W > 0 && x_cs >= C, "mn_nhwc_to_nchw: bad args");
     dim3 grid(mn_cdiv(H * W, 32), mn_cdiv(C, 32), N);
-    nhwc_to_nchw_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(x, x_cs, y, C, H * W);
+    MN_CUDA_CHECK((mn_launch(nhwc_to_nchw_kernel, dim3(grid), dim3(dim3(32, 8)), 0, (cudaStream_t)stream, x, x_cs, y, C, H * W)));
     MN_LAUNCH_CHECK();
     return MN_OK;
 }
