@@ -1,0 +1,75 @@
+"""Self-contained line-restoration flow on top of the three modules.
+
+The reference's ``test_sr.py`` takes character labels and boxes from a third-party YOLO + OCR front-end; the original
+single-model flow uses the encoder's own predictions instead: CTC-style de-duplicated argmax labels (test_w.py:34-40) and
+boxes converted from the encoder's (left, right) pairs to (centre, half-width) exactly as the training model does
+(Train/tspgan/models/tspgan_model.py:331-337).  Integer outputs (labels) are computed on the host, bit-exactly like the
+reference; everything numeric runs through the module API (and therefore through the CUDA kernels).
+"""
+import torch
+
+ALPHABET_SIZE = 6735          # classes [0, 6735) are characters, 6735 is the CTC blank (utils/alphabets.py, test_w.py:38)
+
+
+def decode_labels(logits_row, n_alphabet=ALPHABET_SIZE):
+    """argmax over classes, drop repeats and blanks (reference test_w.py:34-40).  ``logits_row``: [T, 6736]."""
+    idx = torch.max(logits_row.detach(), 1)[1].cpu()
+    out = []
+    for i in range(idx.shape[0]):
+        if not (i > 0 and idx[i - 1] == idx[i]) and idx[i] < n_alphabet:
+            out.append(int(idx[i]))
+    return out
+
+
+def lr_to_center_halfwidth(locs_lr):
+    """(left, right) pairs -> (centre, half-width) pairs, fp32, as Train/tspgan/models/tspgan_model.py:331-337."""
+    out = locs_lr.clone()
+    out[:, 0::2] = (locs_lr[:, 1::2] + locs_lr[:, 0::2]) / 2.0
+    out[:, 1::2] = (locs_lr[:, 1::2] - locs_lr[:, 0::2]) / 2.0
+    return out
+
+
+def load_checkpoint(model, path_or_dict, prefer_ema=True, strict=True):
+    """Load a reference-format checkpoint into one of the three modules.
+
+    Accepts the released files' layout ``{'params': sd}`` (test_sr.py:43-51), BasicSR training checkpoints that also carry
+    ``'params_ema'`` (Train/options/train.yml:69 uses it for the generator), a bare state_dict, and DDP ``module.`` prefixes."""
+    ck = torch.load(path_or_dict, map_location="cpu") if isinstance(path_or_dict, (str, bytes)) or hasattr(path_or_dict, "read") else path_or_dict
+    if isinstance(ck, dict) and ("params" in ck or "params_ema" in ck):
+        key = "params_ema" if (prefer_ema and "params_ema" in ck) else ("params" if "params" in ck else "params_ema")
+        ck = ck[key]
+    sd = {(k[7:] if k.startswith("module.") else k): v for k, v in ck.items()}
+    return model.load_state_dict(sd, strict=strict)
+
+
+@torch.no_grad()
+def restore_lines(encoder, tspgan, sr, lq, labels=None, locs=None, max_chars=16):
+    """LQ lines [B,3,32,512] -> dict(sr, prior, labels, locs, w, logits).
+
+    labels: optional list (per line) of int64 [n_b, 1] tensors; default = the encoder's decoded labels (at most ``max_chars``).
+    locs:   optional [B, 2*n] (centre, half-width) in units of the line width; default = converted encoder boxes."""
+    logits, locs_lr, w = encoder(lq)
+    if labels is None:
+        labels = []
+        for b in range(lq.shape[0]):
+            lab = decode_labels(logits[b])[:max_chars]
+            labels.append(torch.tensor(lab, dtype=torch.long).reshape(-1, 1))
+    if locs is None:
+        locs = lr_to_center_halfwidth(locs_lr)
+    counts = [int(l.shape[0]) for l in labels]
+    total = sum(counts)
+    p64, p32, priors = [], [], []
+    if total > 0:
+        styles = torch.cat([w[b:b + 1].expand(counts[b], -1) for b in range(lq.shape[0]) if counts[b] > 0], dim=0)
+        lab_all = torch.cat([l for l in labels if l.shape[0] > 0], dim=0)
+        img, f64, f32_ = tspgan(styles=styles, labels=lab_all, noise=None)       # one generator call for every character
+        o = 0
+        for n in counts:
+            p64.append(f64[o:o + n]); p32.append(f32_[o:o + n]); priors.append(img[o:o + n]); o += n
+    else:
+        dev = lq.device
+        for _ in counts:
+            p64.append(torch.zeros(0, 256, 64, 64, device=dev)); p32.append(torch.zeros(0, 512, 32, 32, device=dev))
+            priors.append(torch.zeros(0, 3, 128, 128, device=dev))
+    out = sr(lq, p64, p32, locs)
+    return dict(sr=out, prior=priors, labels=labels, locs=locs, w=w, logits=logits)
