@@ -171,7 +171,7 @@ def run_reference_arm(args):
     ms = 1e3 * sum(times) / len(times)
     value = chars / (ms / 1e3)
     rec = {
-        "impl": "reference", "metric": "sr_chars_per_sec", "value": value, "unit": "chars/s", "n_gpus": 0, "steps": steps,
+        "impl": "reference", "metric": "sr_chars_per_sec", "value": value, "unit": "chars/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": f"1 synthetic 32x512 LR line x {chars} chars, encoder->TSPGAN->TSPSRNet (BASELINE configs[1])",
