@@ -6,7 +6,7 @@ struct ConvGeom {
     const float* x; const float* w;
     float* y; float* y2;
     const float* bias; const float* out_scale; const float* residual; const float* y2_scale;
-    const int32_t* valid_w; float* ws;
+    const int32_t* valid_w; float* ws; int64_t ws_bytes;
     const float2* gn_mr; const float* gn_gamma; const float* gn_beta; int gn_swish;   // fused GroupNorm(+swish) on the input (tc2 only)
     int N, H, W, Cin, x_cs;
     int KH, KW, sh, sw, ph, pw, Cout;
@@ -88,6 +88,7 @@ __device__ __forceinline__ void conv_epilogue_vec4(const ConvGeom& g, int m, int
 
 int mn_conv_simt_plan_splits(const ConvGeom& g, int64_t ws_bytes, int requested);
 int mn_conv_simt_launch(ConvGeom g, const float* unused, cudaStream_t st);
+int mn_conv_splitk_reduce_launch(const ConvGeom& g, cudaStream_t st);   // sums g.splits partial tiles in g.ws and runs the fused epilogue
 
 // tcgen05 path (conv_tc.cu)
 int mn_conv_tc_supported(const ConvGeom& g, const char** why);

@@ -200,6 +200,12 @@ int launch_simt(const ConvGeom& g, bool vec_a, bool vec_b, cudaStream_t st) {
 
 }  // namespace
 
+int mn_conv_splitk_reduce_launch(const ConvGeom& g, cudaStream_t st) {
+    const int64_t total = (int64_t)g.M * ((g.Cout + 3) / 4);
+    MN_CUDA_CHECK((mn_launch(conv_splitk_reduce_kernel, dim3((unsigned)mn_cdiv64(total, 256)), dim3(256), 0, st, g)));
+    return MN_OK;
+}
+
 int mn_conv_simt_plan_splits(const ConvGeom& g0, int64_t ws_bytes, int requested) {
     const int bn = g0.Cout > 64 ? 128 : 64;
     const int tiles = mn_cdiv(g0.M, BM) * mn_cdiv(g0.Cout, bn);

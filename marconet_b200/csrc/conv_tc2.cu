@@ -48,6 +48,7 @@ struct Tc2Geom {
     int TW, TH, TN, HWd, HHt, halo_rows, box_bytes, halo_stage_bytes;
     int tiles_w, tiles_h, tiles_n, m_tiles, m_groups, n_tiles;
     int cblocks, taps, KW, ph, pw;
+    int ksplit, cbps;   // split-K over channel blocks for layers with too few tiles: work = (tile, k-slice), cbps channel blocks each
     int bstages, cs;
     const float* wscale;
     int prec;
@@ -86,8 +87,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t crank = cs > 1 ? cluster_ctarank() : 0u;
     const uint16_t cmask = (uint16_t)((1u << cs) - 1u);
     const int cluster_id = blockIdx.x / cs, num_clusters = gridDim.x / cs;
-    const int total_work = t.m_groups * t.n_tiles;
+    const int total_work = t.m_groups * t.n_tiles * t.ksplit;
     const int BS = t.bstages;
+    // work item -> (k-slice, channel tile, pixel-tile group); identical in every warp role
+    auto work_ks = [&](int work) { return work % t.ksplit; };
+    auto work_nt = [&](int work) { return (work / t.ksplit) % t.n_tiles; };
+    auto work_mg = [&](int work) { return work / (t.ksplit * t.n_tiles); };
 
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -113,7 +118,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     auto tile_origin = [&](int work, int& n0, int& oy0, int& ox0) {
-        int m_tile = (work / t.n_tiles) * cs + (int)crank;
+        int m_tile = work_mg(work) * cs + (int)crank;
         if (m_tile >= t.m_tiles) { n0 = g.N + 1024; oy0 = 0; ox0 = 0; return; }   // padding CTA of a cluster: everything out of bounds
         const int tw_i = m_tile % t.tiles_w; m_tile /= t.tiles_w;
         const int th_i = m_tile % t.tiles_h; m_tile /= t.tiles_h;
@@ -126,8 +131,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int rows = NT / cs;
         const uint32_t dst0 = smem_base + off_b + crank * rows * 128;
         for (int work = cluster_id; work < total_work; work += num_clusters) {
-            const int row0 = (work % t.n_tiles) * NT + (int)crank * rows;
-            for (int cb = 0; cb < t.cblocks; ++cb) {
+            const int row0 = work_nt(work) * NT + (int)crank * rows;
+            const int cb0 = work_ks(work) * t.cbps;
+            for (int cb = cb0; cb < cb0 + t.cbps; ++cb) {
                 for (int tap = 0; tap < t.taps; ++tap) {
                     mbar_wait(bar(I_BE + s), ph ^ 1);
                     if (elect_one_sync()) {
@@ -152,7 +158,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int work = cluster_id; work < total_work; work += num_clusters) {
             int n0, oy0, ox0;
             tile_origin(work, n0, oy0, ox0);
-            for (int cb = 0; cb < t.cblocks; ++cb) {
+            const int cb0 = work_ks(work) * t.cbps;
+            for (int cb = cb0; cb < cb0 + t.cbps; ++cb) {
                 mbar_wait(bar(I_HE + hs), ph ^ 1);
                 if (elect_one_sync()) {
                     mbar_expect_tx(bar(I_HF + hs), 2u * t.halo_rows * 128u);
@@ -177,13 +184,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         // The tensor core truncates (toward zero) every time it adds into the fp32 accumulator: measured mean shrink of the
         // main accumulator = 1.56e-8 per accumulation step, sign-symmetric, independent of K (tools/probe_tc_bias.py).  Undo the
         // expected shrink of D (K/16 steps); Dc is 2^-11 of the result and needs nothing.
-        const float dfix = 1.f + 1.5e-8f * (float)(t.taps * t.cblocks * (KB / 16));
+        const float dfix = 1.f + 1.5e-8f * (float)(t.taps * t.cbps * (KB / 16));
         const int tn = r / (t.TH * t.TW);
         const int rem = r - tn * (t.TH * t.TW);
         const int th = rem / t.TW, tw = rem - th * t.TW;
         uint32_t ecnt = 0;
         auto epilogue = [&](int work) {
-            const int nt_i = work % t.n_tiles;
+            const int nt_i = work_nt(work);
+            const int ks = work_ks(work);
             int n0, oy0, ox0;
             tile_origin(work, n0, oy0, ox0);
             {
@@ -250,7 +258,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         if (m >= 0) {
                             const int nn = rowm[128 + row];
                             const float4 u = *reinterpret_cast<const float4*>(stg + row * STG_PITCH + col);
-                            conv_epilogue_vec4(g, m, nn & 0x3FFFFFFF, (nn >> 30) != 0, o, u, bias4);
+                            if (t.ksplit > 1)      // raw partial sum of this k-slice; conv_splitk_reduce_kernel adds the slices and runs the epilogue
+                                *reinterpret_cast<float4*>(g.ws + ((size_t)ks * g.M + m) * g.Cout + o) = u;
+                            else
+                                conv_epilogue_vec4(g, m, nn & 0x3FFFFFFF, (nn >> 30) != 0, o, u, bias4);
                         }
                     }
                 }
@@ -259,7 +270,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         };
         // The epilogue of tile i runs after the first two halo tiles of tile i+1 have been split, so the feed/MMA warps have
         // ~2 x taps k-blocks of work queued while these warps drain TMEM and store tile i.
-        const int epi_after_cb = t.cblocks > 1 ? 1 : 0;
+        const int epi_after_cb = t.cbps > 1 ? 1 : 0;
         int prev_work = -1;
         uint32_t hs = 0, hph = 0;
         constexpr bool gn = GN;       // fused GroupNorm(+swish) input transform: separate instantiation, zero cost when off
@@ -267,7 +278,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int work = cluster_id; work < total_work; work += num_clusters) {
             int hn0 = 0, hoy0 = 0, hox0 = 0;
             if (gn) tile_origin(work, hn0, hoy0, hox0);
-            for (int cb = 0; cb < t.cblocks; ++cb) {
+            const int cb0 = work_ks(work) * t.cbps;
+            for (int cbi = 0; cbi < t.cbps; ++cbi) {
+                const int cb = cb0 + cbi;
                 if (gn) {   // per-channel affine of this 64-channel block -> smem (the previous block's readers are past their rows)
                     named_bar_sync(2, 128);
                     if (sidx < 64) gnp[sidx] = g.gn_gamma[cb * KB + sidx];
@@ -337,7 +350,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // these generic writes precede the next TMA refill
                 mbar_arrive(bar(I_SD + hs));
                 hs ^= 1; if (hs == 0) hph ^= 1;
-                if (cb == epi_after_cb && prev_work >= 0) epilogue(prev_work);
+                if (cbi == epi_after_cb && prev_work >= 0) epilogue(prev_work);
             }
             prev_work = work;
         }
@@ -347,7 +360,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const uint32_t fmt = (t.prec == MN_PREC_BF16X3_TC) ? 1u : 0u;
         const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const bool three = t.prec != MN_PREC_F16X1_TC;
-        const int num_kb = t.cblocks * t.taps;
+        const int num_kb = t.cbps * t.taps;
         const uint64_t desc_hi0 = make_b_desc(smem_base + off_b);           // stage 0, hi plane, k-step 0
         uint32_t as = 0, aph = 0, bs = 0, bph = 0, tcnt = 0;
         for (int work = cluster_id; work < total_work; work += num_clusters, ++tcnt) {
@@ -391,7 +404,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int rho0 = tn < t.TN ? (tn * t.HHt + th) * t.HWd + tw : 0;   // halo row of tap (0,0); unused MMA rows read row 0
         uint32_t hs = 0, hph = 0, as = 0, aph = 0;
         for (int work = cluster_id; work < total_work; work += num_clusters) {
-            for (int cb = 0; cb < t.cblocks; ++cb) {
+            for (int cb = 0; cb < t.cbps; ++cb) {
                 mbar_wait(bar(I_SD + hs), hph);
                 const uint8_t* halo = smem + hs * t.halo_stage_bytes;
                 int ky = 0, kx = 0;
@@ -499,6 +512,16 @@ Tc2Plan plan_tc2(const ConvGeom& g) {
     if (t.cs != 1 && t.cs != 2 && t.cs != 4) t.cs = 1;
     if ((p.NT / t.cs) % 8 != 0) t.cs = 1;
     t.m_groups = (t.m_tiles + t.cs - 1) / t.cs;
+    // split-K: few tiles but a deep K loop (4x4 / 8x8 generator layers, ResNet stages at batch 1) -> spread the channel blocks of
+    // a tile over several CTAs; partial sums go to the caller's workspace and conv_splitk_reduce_kernel finishes the job.
+    t.ksplit = 1;
+    {
+        const int items = t.m_groups * t.n_tiles, slots = mn_num_sms() / t.cs;
+        while (t.ksplit * 2 * items <= slots && t.cblocks % (t.ksplit * 2) == 0 && t.cblocks / (t.ksplit * 2) >= 1 && t.ksplit < 8) t.ksplit *= 2;
+        while (t.ksplit > 1 && (int64_t)t.ksplit * g.M * g.Cout * 4 > g.ws_bytes) t.ksplit >>= 1;
+        if (t.ksplit > 1 && (!g.ws || g.gn_mr || (g.Cout & 3))) t.ksplit = 1;
+    }
+    t.cbps = t.cblocks / t.ksplit;
     const int fixed = 2 * t.halo_stage_bytes + STG_BYTES + 1024 + 512 + 256 + 1024;
     int bs = (SMEM_LIMIT - fixed) / (2 * p.NT * 128);
     if (bs > MAX_BSTAGES) bs = MAX_BSTAGES;
@@ -517,7 +540,7 @@ int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mbh, const CUtensorMap&
         smem_set = SMEM_LIMIT;
     }
     const Tc2Geom& t = p.t;
-    const int total_work = t.m_groups * t.n_tiles;
+    const int total_work = t.m_groups * t.n_tiles * t.ksplit;
     int sms = mn_num_sms();
     if (mn_max_ctas() > 0 && mn_max_ctas() < sms) sms = mn_max_ctas();
     int clusters = sms / t.cs;
@@ -579,6 +602,11 @@ int mn_conv_tc2_launch(const ConvGeom& g, const void* w_hi, const void* w_lo, co
     }
     t.wscale = w_scale + 1;
     t.prec = prec;
-    if (g.gn_mr) return p.NT == 128 ? launch_tc2<128, true>(ma, mbh, mbl, g, p, st) : launch_tc2<64, true>(ma, mbh, mbl, g, p, st);
-    return p.NT == 128 ? launch_tc2<128, false>(ma, mbh, mbl, g, p, st) : launch_tc2<64, false>(ma, mbh, mbl, g, p, st);
+    int rc;
+    if (g.gn_mr) rc = p.NT == 128 ? launch_tc2<128, true>(ma, mbh, mbl, g, p, st) : launch_tc2<64, true>(ma, mbh, mbl, g, p, st);
+    else rc = p.NT == 128 ? launch_tc2<128, false>(ma, mbh, mbl, g, p, st) : launch_tc2<64, false>(ma, mbh, mbl, g, p, st);
+    if (rc != MN_OK || t.ksplit == 1) return rc;
+    ConvGeom gr = g;
+    gr.splits = t.ksplit;
+    return mn_conv_splitk_reduce_launch(gr, st);
 }

@@ -48,6 +48,8 @@ TC_CASES = [
     (3, 8, 16, 64, 128, 3),       # odd number of pixel tiles: padding CTA inside a 2-CTA cluster
     (1, 64, 1024, 64, 64, 3),     # 512 pixel tiles: several work items per persistent CTA
     (1, 16, 512, 128, 256, 1),    # 1x1 on a wide map, two N tiles
+    (4, 8, 8, 512, 512, 3),       # few tiles, deep K: split-K over channel blocks + reduce kernel
+    (1, 8, 512, 256, 256, 3),     # ResNet stage at batch 1 (split-K 2)
 ]
 # tensor-core fp32 accumulation truncates (round-toward-zero): the error grows ~linearly with K/16 accumulation steps
 TOL = {"f16x3": 4e-5, "bf16x3": 2e-4, "f16x1": 4e-3}
