@@ -57,6 +57,11 @@ int mn_version(void);
 /* Cap the number of CTAs the persistent tensor-core kernels launch (0 = one per SM).  Leaving a few SMs free lets NCCL's
  * copy kernels run beside them, so an asynchronous all-gather overlaps the next chunk of compute.  Returns the old value. */
 int mn_set_max_ctas(int n);
+
+/* Programmatic dependent launch (every kernel is launched with the programmatic-stream-serialization attribute so that its
+ * launch overlaps the previous kernel's tail).  mn_set_pdl(0) turns the attribute off process-wide (returns the old
+ * setting); the environment variable MN_PDL=0 does the same at load time. */
+int mn_set_pdl(int on);
 /* 1 when the current device is compute capability 10.x (tcgen05/TMA paths usable). */
 int mn_device_is_sm100(void);
 
@@ -127,6 +132,11 @@ int mn_pixelnorm(const float* x, float* y, int N, int C, void* stream);
  * labels are int64 on the DEVICE and must already be range-checked by the host. */
 int mn_select_text(const float* emb, const int64_t* labels, const float* s, int s_stride,
                    float* out, int N, int L, int C, void* stream);
+
+/* Device-side range check of the character labels (the reference fails on the empty embedding slice at
+ * models/networks.py:211): clamped[i] = clamp(labels[i], 0, classes-1); bit 0 of *err is raised when any label was out
+ * of range.  For callers that must not touch the host between launches (CUDA-graph capture). */
+int mn_check_labels(const int64_t* labels, int64_t* clamped, int n, int classes, int32_t* err, void* stream);
 
 /* Demodulation factors, models/networks.py:284-287 restated on the shared weight:
  *   demod[n][o] = rsqrt( sum_c s[n][c]^2 * wsq[c][o] + 1e-8 ),
@@ -199,6 +209,15 @@ int mn_adain_concat(const float* prior, int prior_cs, const float* feat, int fea
 int mn_window_scatter(const float* feat, int feat_cs, const float* scale, const float* shift,
                       const int32_t* owner, const mn_window* win, float* out, int out_cs,
                       int B, int H, int W, int Wp, int C, void* stream);
+
+/* The window integers of models/networks.py:426-441 / :460-474 computed on the device (no host round trip):
+ *   center = (int)(locs[b*locs_stride + 2c] * W)   (fp32 multiply, truncation), x1 = max(center-half,0) as coded,
+ *   x2 = min(center+half, W), y1 = half - (x2-x1)/2; valid[i] = x2-x1; owner[b*W+x] = last character whose window
+ *   covers column x, else -1.  Characters of line b are win[line_first[b] .. line_first[b+1]) (device int32[B+1]);
+ *   max_chars >= the longest line.  An empty window (reference: error at networks.py:443) raises bit 1 of *err and
+ *   becomes a zero-width window. */
+int mn_char_windows(const float* locs, int locs_stride, const int32_t* line_first, int B, int max_chars, int W, int half,
+                    mn_window* win, int32_t* valid, int32_t* owner, int32_t* err, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * TextViT operators

@@ -1,4 +1,5 @@
 // Error reporting, version and device queries of the C ABI (include/marconet_b200.h).
+#include <cstdlib>
 #include <stdarg.h>
 #include <string.h>
 #include "mn_common.cuh"
@@ -29,6 +30,17 @@ int mn_max_ctas() { return g_max_ctas; }
 extern "C" int mn_set_max_ctas(int n) {
     const int old = g_max_ctas;
     g_max_ctas = n > 0 ? n : 0;
+    return old;
+}
+
+static int g_pdl = -1;
+int mn_pdl_enabled() {
+    if (g_pdl < 0) { const char* e = getenv("MN_PDL"); g_pdl = (e && e[0] == '0') ? 0 : 1; }
+    return g_pdl;
+}
+extern "C" int mn_set_pdl(int on) {
+    const int old = mn_pdl_enabled();
+    g_pdl = on ? 1 : 0;
     return old;
 }
 

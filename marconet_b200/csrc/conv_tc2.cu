@@ -558,7 +558,7 @@ int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mbh, const CUtensorMap&
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     static int pdl = -1;
     if (pdl < 0) { const char* e = getenv("MN_TC_PDL"); pdl = (e && e[0] == '0') ? 0 : 1; }
-    cfg.attrs = attr; cfg.numAttrs = pdl ? 2 : 1;
+    cfg.attrs = attr; cfg.numAttrs = (pdl && mn_pdl_enabled()) ? 2 : 1;
     MN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<NT, GN>, ma, mbh, mbl, g, t));
     return MN_OK;
 }

@@ -64,6 +64,7 @@ __device__ __forceinline__ void mn_pdl_prologue() {
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
+int mn_pdl_enabled();   // programmatic dependent launch on (default) / off (mn_set_pdl(0) or MN_PDL=0)
 template <typename... KArgs, typename... Args>
 static inline cudaError_t mn_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
     cudaLaunchConfig_t cfg{};
@@ -71,7 +72,7 @@ static inline cudaError_t mn_launch(void (*kernel)(KArgs...), dim3 grid, dim3 bl
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.attrs = attr; cfg.numAttrs = mn_pdl_enabled() ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

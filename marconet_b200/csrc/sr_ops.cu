@@ -25,12 +25,23 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
     double ds = 0.0, dss = 0.0;
     int cnt = 0;
     if (my_p < ppi) {
-        for (int p = p_begin + my_p; p < p_end; p += ppi) {
-            if (valid_w && (p % W) >= wv) continue;
-            const float4 v = *reinterpret_cast<const float4*>(xn + (size_t)p * x_cs);
-            s += (v.x + v.y) + (v.z + v.w);
-            ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
-            if (++cnt == 32) { ds += (double)s; dss += (double)ss; s = 0.f; ss = 0.f; cnt = 0; }
+        // 4 pixels per trip: the four 128-bit loads are issued before any of them is consumed
+        for (int p = p_begin + my_p; p < p_end; p += 4 * ppi) {
+            float4 v[4];
+            bool on[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int pk = p + k * ppi;
+                on[k] = pk < p_end && !(valid_w && (pk % W) >= wv);
+                v[k] = on[k] ? *reinterpret_cast<const float4*>(xn + (size_t)pk * x_cs) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (!on[k]) continue;
+                s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+                ss = fmaf(v[k].x, v[k].x, ss); ss = fmaf(v[k].y, v[k].y, ss); ss = fmaf(v[k].z, v[k].z, ss); ss = fmaf(v[k].w, v[k].w, ss);
+                if (++cnt == 32) { ds += (double)s; dss += (double)ss; s = 0.f; ss = 0.f; cnt = 0; }
+            }
         }
     }
     ds += (double)s; dss += (double)ss;
@@ -67,38 +78,61 @@ __global__ void gn_finalize_kernel(const double* __restrict__ stats, float2* __r
     mr[i] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
 }
 
-__global__ void gn_apply_kernel(const float* __restrict__ x, int x_cs, float* __restrict__ y, int y_cs,
+// One thread normalises 4 channels of GN_PPT pixels (pixel stride = a quarter of the tensor, so every warp access stays a
+// contiguous run of channels); all loads are issued before the first use.  Measured 3.4-3.9 TB/s; a capped grid-stride
+// variant (8 CTAs/SM) was slower (2.7-3.0 TB/s: 56 registers leave only 4 resident CTAs), one item per thread 3.1-3.4.
+constexpr int GN_PPT = 4;
+__global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x, int x_cs, float* __restrict__ y, int y_cs,
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 int N, int H, int W, int C, int cpg, float eps, int swish,
-                                const int32_t* __restrict__ valid_w, const float2* __restrict__ mr) {
+                                const int32_t* __restrict__ valid_w, const float2* __restrict__ mr, uint32_t pix_stride) {
     mn_pdl_prologue();
     const int c4 = C >> 2;
-    const int64_t total = (int64_t)N * H * W * c4;
-    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;     // host guarantees total < 2^31: 32-bit div/mod only
-    if (idx >= (uint32_t)total) return;
+    const uint32_t npix = (uint32_t)N * H * W;
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;     // host guarantees N*H*W*C/4 < 2^31: 32-bit div/mod only
+    if (idx >= pix_stride * (uint32_t)c4) return;
     const int c = (int)(idx % c4) * 4;
-    const uint32_t pix = idx / c4;
-    const int px = (int)(pix % W);
-    const int n = (int)(pix / (uint32_t)(H * W));
-    const int wv = valid_w ? valid_w[n] : W;
-    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (px < wv) {
-        const int G = C / cpg, g = c / cpg;
-        const float2 m2 = mr[(size_t)n * G + g];
-        const float mean = m2.x, rstd = m2.y;
-        const float4 v = *reinterpret_cast<const float4*>(x + (size_t)pix * x_cs + c);
-        const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
-        const float gam[4] = {ga.x, ga.y, ga.z, ga.w}, bet[4] = {be.x, be.y, be.z, be.w};
-        float t[4] = {v.x, v.y, v.z, v.w};
+    const uint32_t pix0 = idx / c4;
+    const int G = C / cpg, g = c / cpg;
+    const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
+    const float gam[4] = {ga.x, ga.y, ga.z, ga.w}, bet[4] = {be.x, be.y, be.z, be.w};
+    float4 v[GN_PPT];
+    float2 m2[GN_PPT];
+    bool live[GN_PPT], on[GN_PPT];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float u = (t[j] - mean) * rstd * gam[j] + bet[j];
-            if (swish) u = u * (1.f / (1.f + expf(-u)));
-            t[j] = u;
+    for (int k = 0; k < GN_PPT; ++k) {
+        const uint32_t pix = pix0 + (uint32_t)k * pix_stride;
+        live[k] = pix < npix;
+        on[k] = false;
+        v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        m2[k] = make_float2(0.f, 0.f);
+        if (live[k]) {
+            const int px = (int)(pix % W);
+            const int n = (int)(pix / (uint32_t)(H * W));
+            on[k] = px < (valid_w ? valid_w[n] : W);
+            if (on[k]) {
+                v[k] = *reinterpret_cast<const float4*>(x + (size_t)pix * x_cs + c);
+                m2[k] = mr[(size_t)n * G + g];
+            }
         }
-        o = make_float4(t[0], t[1], t[2], t[3]);
     }
-    *reinterpret_cast<float4*>(y + (size_t)pix * y_cs + c) = o;
+#pragma unroll
+    for (int k = 0; k < GN_PPT; ++k) {
+        if (!live[k]) continue;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (on[k]) {
+            const float mean = m2[k].x, rstd = m2[k].y;
+            float t[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float u = (t[j] - mean) * rstd * gam[j] + bet[j];
+                if (swish) u = u * (1.f / (1.f + expf(-u)));
+                t[j] = u;
+            }
+            o = make_float4(t[0], t[1], t[2], t[3]);
+        }
+        *reinterpret_cast<float4*>(y + (size_t)(pix0 + (uint32_t)k * pix_stride) * y_cs + c) = o;
+    }
 }
 
 // ---------------------------------------------------------------- AdaIN + concat
@@ -237,6 +271,39 @@ __global__ void window_scatter_kernel(const float* __restrict__ feat, int feat_c
     *reinterpret_cast<float4*>(out + (size_t)pix * out_cs + c) = o;
 }
 
+// ---------------------------------------------------------------- window integers on the device (networks.py:426-441 / :460-474)
+// One CTA per LR line.  Phase 1: one thread per character computes (x1, x2, y1) with the reference's arithmetic
+// (fp32 multiply, truncation toward zero).  Phase 2: one thread per column finds its owner = the LAST character in
+// program order whose window covers it (networks.py:448,481).  An empty window (the reference dies on the empty slice
+// at networks.py:443) raises bit 1 of *err and is replaced by a zero-width window so that no consumer reads out of bounds.
+__global__ void char_windows_kernel(const float* __restrict__ locs, int locs_stride, const int32_t* __restrict__ line_first,
+                                    int W, int half, mn_window* __restrict__ win, int32_t* __restrict__ valid,
+                                    int32_t* __restrict__ owner, int32_t* __restrict__ err) {
+    mn_pdl_prologue();
+    extern __shared__ int32_t sw[];            // [n][2] = x1, x2 of this line's characters
+    const int b = blockIdx.x;
+    const int first = line_first[b], n = line_first[b + 1] - first;
+    for (int c = threadIdx.x; c < n; c += blockDim.x) {
+        const int center = __float2int_rz(__fmul_rn(locs[(size_t)b * locs_stride + 2 * c], (float)W));
+        int x1 = center < half ? 0 : center - half;
+        int x2 = center + half > W ? W : center + half;
+        int wv = x2 - x1;
+        if (wv <= 0 || x1 >= W) { atomicOr(err, 2); x1 = 0; x2 = 0; wv = 0; }
+        mn_window w;
+        w.line = b; w.x1 = x1; w.x2 = x2; w.y1 = half - wv / 2;
+        win[first + c] = w;
+        valid[first + c] = wv;
+        sw[2 * c] = x1; sw[2 * c + 1] = x2;
+    }
+    __syncthreads();
+    for (int x = threadIdx.x; x < W; x += blockDim.x) {
+        int o = -1;
+        for (int c = 0; c < n; ++c)
+            if (x >= sw[2 * c] && x < sw[2 * c + 1]) o = first + c;
+        owner[(size_t)b * W + x] = o;
+    }
+}
+
 }  // namespace
 
 static int gn_check(const float* x, int x_cs, int N, int H, int W, int C, int cpg) {
@@ -256,7 +323,7 @@ extern "C" int mn_groupnorm_stats(const float* x, int x_cs, int N, int H, int W,
     MN_CUDA_CHECK(cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * N * G, st));
     const int HW = H * W;
     int blocks = mn_cdiv(mn_num_sms() * 8, N);
-    if (blocks > mn_cdiv(HW, 64)) blocks = mn_cdiv(HW, 64);
+    if (blocks > mn_cdiv(HW, 32)) blocks = mn_cdiv(HW, 32);
     if (blocks < 1) blocks = 1;
     const int ppb = mn_cdiv(HW, blocks);
     blocks = mn_cdiv(HW, ppb);
@@ -275,8 +342,9 @@ extern "C" int mn_groupnorm_apply(const float* x, int x_cs, float* y, int y_cs, 
     MN_REQUIRE(y && gamma && beta && mean_rstd && (y_cs & 3) == 0 && ((uintptr_t)y & 15) == 0, "mn_groupnorm_apply: bad args");
     const int64_t total = (int64_t)N * H * W * (C >> 2);
     MN_REQUIRE(total < (1ll << 31), "tensor too large for 32-bit indexing");
-    MN_CUDA_CHECK((mn_launch(gn_apply_kernel, dim3((unsigned)mn_cdiv64(total, 256)), dim3(256), 0, (cudaStream_t)stream, x, x_cs, y, y_cs, gamma, beta, N, H, W, C, cpg, 0.f, swish, valid_w,
-                                                                                    reinterpret_cast<const float2*>(mean_rstd))));
+    const uint32_t pix_stride = (uint32_t)mn_cdiv64((int64_t)N * H * W, GN_PPT);
+    MN_CUDA_CHECK((mn_launch(gn_apply_kernel, dim3((unsigned)mn_cdiv64((int64_t)pix_stride * (C >> 2), 256)), dim3(256), 0, (cudaStream_t)stream, x, x_cs, y, y_cs, gamma, beta, N, H, W, C, cpg, 0.f, swish, valid_w,
+                             reinterpret_cast<const float2*>(mean_rstd), pix_stride)));
     MN_LAUNCH_CHECK();
     return MN_OK;
 }
@@ -325,6 +393,16 @@ extern "C" int mn_window_scatter(const float* feat, int feat_cs, const float* sc
     const int64_t total = (int64_t)B * H * W * (C >> 2);
     MN_REQUIRE(total < (1ll << 31), "tensor too large for 32-bit indexing");
     MN_CUDA_CHECK((mn_launch(window_scatter_kernel, dim3((unsigned)mn_cdiv64(total, 256)), dim3(256), 0, (cudaStream_t)stream, feat, feat_cs, scale, shift, owner, win, out, out_cs, B, H, W, Wp, C)));
+    MN_LAUNCH_CHECK();
+    return MN_OK;
+}
+
+extern "C" int mn_char_windows(const float* locs, int locs_stride, const int32_t* line_first, int B, int max_chars, int W, int half,
+                               mn_window* win, int32_t* valid, int32_t* owner, int32_t* err, void* stream) {
+    MN_REQUIRE(locs && line_first && win && valid && owner && err, "mn_char_windows: null pointer");
+    MN_REQUIRE(B > 0 && W > 0 && half > 0 && max_chars >= 0 && max_chars <= 4096, "mn_char_windows: bad dims");
+    MN_CUDA_CHECK((mn_launch(char_windows_kernel, dim3(B), dim3(256), (size_t)max_chars * 2 * sizeof(int32_t), (cudaStream_t)stream,
+                             locs, locs_stride, line_first, W, half, win, valid, owner, err)));
     MN_LAUNCH_CHECK();
     return MN_OK;
 }

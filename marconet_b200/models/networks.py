@@ -251,12 +251,17 @@ class TextGenerator(_PackedModule):
         n, l = labels.shape
         if styles.shape[0] != n:
             raise RuntimeError("styles and labels disagree on the number of characters")
-        lab_host = labels.detach().to("cpu", torch.int64)
-        if n * l > 0 and (int(lab_host.min()) < 0 or int(lab_host.max()) >= pk["emb"].shape[0]):
-            raise IndexError(f"character label out of range [0, {pk['emb'].shape[0]}) "
-                             f"(reference: empty embedding slice, networks.py:211)")
-        lab_dev = labels.to(dev, torch.int64).contiguous().reshape(-1) if labels.is_cuda else \
-            lab_host.reshape(-1).to(dev, non_blocking=False)
+        flag = ops.deferred_flag()
+        if flag is not None and labels.is_cuda:
+            # no host round trip (CUDA-graph capture): range check + clamp on the device, error bit read back by the caller
+            lab_dev = ops.check_labels(labels.to(torch.int64).contiguous().reshape(-1), pk["emb"].shape[0], flag)
+        else:
+            lab_host = labels.detach().to("cpu", torch.int64)
+            if n * l > 0 and (int(lab_host.min()) < 0 or int(lab_host.max()) >= pk["emb"].shape[0]):
+                raise IndexError(f"character label out of range [0, {pk['emb'].shape[0]}) "
+                                 f"(reference: empty embedding slice, networks.py:211)")
+            lab_dev = labels.to(dev, torch.int64).contiguous().reshape(-1) if labels.is_cuda else \
+                lab_host.reshape(-1).to(dev, non_blocking=False)
 
         z = ops.pixelnorm(styles.float().contiguous())
         for w, b in pk["mlp"]:
@@ -434,6 +439,7 @@ class TSPSRNet(_PackedModule):
         self.conv_64_shift = nn.Sequential(_SNConv(d, d), act(), _SNConv(d, d))
         self.conv_64_fuse = nn.Sequential(ResTextBlockV2(2 * d, d))
         self.dim = d
+        self._line_first_cache = {}
 
     def _pack(self, device):
         pk = {}
@@ -454,19 +460,37 @@ class TSPSRNet(_PackedModule):
         pk["fuse64"] = self.conv_64_fuse[0].packed()
         return pk
 
-    def _fuse(self, pk, lvl, feat, prior, locs_host, counts, half):
-        """Per-character prior fusion of one level as ONE ragged batch (reference loops :425-448/:459-481)."""
+    def _line_first(self, counts, dev):
+        """Device int32[B+1] prefix sums of the per-line character counts (cached: constant for a captured graph)."""
+        key = (tuple(counts), dev)
+        t = self._line_first_cache.get(key)
+        if t is None:
+            pre = [0]
+            for n in counts:
+                pre.append(pre[-1] + n)
+            t = torch.tensor(pre, dtype=torch.int32).to(dev)
+            self._line_first_cache[key] = t
+        return t
+
+    def _fuse(self, pk, lvl, feat, prior, locs, counts, half):
+        """Per-character prior fusion of one level as ONE ragged batch (reference loops :425-448/:459-481).
+        ``locs`` is a CPU tensor (eager checks) or, inside ops.deferred_checks, the device tensor itself."""
         dev = feat.device
         b, h, w, c = feat.shape
-        wins, valid, owner = char_windows(locs_host, counts, w, half)
-        nc = len(wins)
+        nc = sum(counts)
         if nc == 0:
             return feat
         wp = 2 * half
-        win_dev = torch.tensor(wins, dtype=torch.int32).to(dev)
-        valid_dev = torch.tensor(valid, dtype=torch.int32).to(dev)
-        owner_dev = torch.tensor(owner, dtype=torch.int32).to(dev)
-        vw = valid_dev if min(valid) < wp else None       # full-width windows need no masking
+        flag = ops.deferred_flag()
+        if flag is not None and locs.is_cuda:
+            win_dev, valid_dev, owner_dev = ops.char_windows(locs, self._line_first(counts, dev), counts, w, half, flag)
+            vw = valid_dev                                # widths are not known on the host: always mask
+        else:
+            wins, valid, owner = char_windows(locs, counts, w, half)
+            win_dev = torch.tensor(wins, dtype=torch.int32).to(dev)
+            valid_dev = torch.tensor(valid, dtype=torch.int32).to(dev)
+            owner_dev = torch.tensor(owner, dtype=torch.int32).to(dev)
+            vw = valid_dev if min(valid) < wp else None   # full-width windows need no masking
         fin = ops.adain_concat(prior, feat, win_dev, nc, wp)                         # [Nc,H,wp,2C]
         fuse = _res_block(pk[f"fuse{lvl}"], fin, vw)
         scale = _two(pk[f"conv_{lvl}_scale"], fuse, vw)
@@ -504,7 +528,10 @@ class TSPSRNet(_PackedModule):
         counts = [int(p.shape[0]) for p in priors32] + [0] * (bsz - len(priors32))
         if [int(p.shape[0]) for p in priors64] != counts[:len(priors64)]:
             raise RuntimeError("priors64 / priors32 disagree on the number of characters")
-        locs_host = locs.detach().to("cpu", torch.float32)
+        if ops.deferred_flag() is not None and locs.is_cuda:
+            locs_host = locs.detach().float().contiguous()      # stays on the device; windows come from mn_char_windows
+        else:
+            locs_host = locs.detach().to("cpu", torch.float32)
 
         x = ops.nchw_to_nhwc(lq.float())
         h, w = x.shape[1], x.shape[2]

@@ -219,6 +219,72 @@ def pixelnorm(x):
     return y
 
 
+# ---- deferred error checks (CUDA-graph capture / pipelined callers) -----------------------------------
+# The module API raises on a bad label or an empty character window BEFORE launching, which costs a device->host round
+# trip per call.  Inside ``deferred_checks(flag)`` the same conditions are evaluated by device kernels that OR a bit into
+# ``flag`` (int32[1] on the device: bit 0 = label out of range, bit 1 = empty window); the caller reads it with the results.
+_DEFERRED_FLAG = None
+ERR_LABEL, ERR_WINDOW = 1, 2
+
+
+class deferred_checks:
+    def __init__(self, flag):
+        if flag is not None and (flag.dtype != torch.int32 or not flag.is_cuda or flag.numel() != 1):
+            raise RuntimeError("deferred_checks: flag must be an int32[1] CUDA tensor")
+        self.flag, self.prev = flag, None
+
+    def __enter__(self):
+        global _DEFERRED_FLAG
+        self.prev, _DEFERRED_FLAG = _DEFERRED_FLAG, self.flag
+        return self.flag
+
+    def __exit__(self, *exc):
+        global _DEFERRED_FLAG
+        _DEFERRED_FLAG = self.prev
+        return False
+
+
+def deferred_flag():
+    return _DEFERRED_FLAG
+
+
+def raise_deferred(flag_value):
+    """Turn a flag value read back from the device into the exception the eager path raises."""
+    if flag_value & ERR_LABEL:
+        raise IndexError("character label out of range (reference: empty embedding slice, networks.py:211)")
+    if flag_value & ERR_WINDOW:
+        raise RuntimeError("empty character window (the reference fails on the empty slice at networks.py:443)")
+
+
+def check_labels(labels_dev, classes, flag):
+    """labels_dev: int64 [n] on the device -> clamped copy; raises bit 0 of ``flag`` on the device when out of range."""
+    global LAUNCHES
+    n = labels_dev.numel()
+    out = torch.empty_like(labels_dev)
+    _lib.check(_lib.load().mn_check_labels(_ptr(labels_dev), _ptr(out), n, classes, _ptr(flag), _stream()), "mn_check_labels")
+    LAUNCHES += 1
+    return out
+
+
+def char_windows(locs_dev, line_first_dev, counts, width, half, flag):
+    """Device restatement of models.networks.char_windows: returns (win int32[Nc,4], valid int32[Nc], owner int32[B,W])."""
+    global LAUNCHES
+    _require_cuda(locs_dev, "locs")
+    if locs_dev.dtype != torch.float32 or locs_dev.dim() != 2 or locs_dev.stride(1) != 1:
+        raise RuntimeError("char_windows: locs must be fp32 [B, 2n] with unit inner stride")
+    b, nc = len(counts), sum(counts)
+    if locs_dev.shape[0] < b or (counts and locs_dev.shape[1] < 2 * max(counts)):
+        raise RuntimeError("char_windows: locs has fewer entries than characters")
+    dev = locs_dev.device
+    win = torch.empty((nc, 4), dtype=torch.int32, device=dev)
+    valid = torch.empty((nc,), dtype=torch.int32, device=dev)
+    owner = torch.empty((b, width), dtype=torch.int32, device=dev)
+    _lib.check(_lib.load().mn_char_windows(_ptr(locs_dev), locs_dev.stride(0), _ptr(line_first_dev), b, max(counts), width, half,
+                                           _ptr(win), _ptr(valid), _ptr(owner), _ptr(flag), _stream()), "mn_char_windows")
+    LAUNCHES += 1
+    return win, valid, owner
+
+
 def select_text(emb, labels_dev, s, n, l):
     """emb: [classes, C]; labels_dev: int64 [n*l] on device; s: [n, C] view (row stride s.stride(0)) or None."""
     global LAUNCHES
