@@ -232,6 +232,16 @@ int mn_layernorm(const float* x, float* y, const float* gamma, const float* beta
 int mn_linear_small_m(const float* x, const float* w, const float* bias, const float* residual, float* y,
                       int M, int K, int N, int act, float gain, void* stream);
 
+/* The same layer over a GATHERED x and `batches` independent row blocks (text lines): element (r, k) of batch z is
+ *   x[z*x_batch_stride + r*x_row_stride + (k / x_seg_len)*x_seg_stride + k % x_seg_len]      (x_seg_len % 32 == 0),
+ * y is dense [batches][M][N]; residual (optional) is [M][N] per batch at residual + z*res_batch_stride (0 = shared).
+ * This is the TextViT patch embedding (models/textvit_arch.py:33-36: Rearrange 'b c (h p1) (w p2) -> b h w (p1 p2 c)' +
+ * Linear(32768, 512) + positional embedding) reading the NHWC ResNet feature map [B,8,512,512] in place:
+ *   M = 64 tokens, K = 8*8*512, x_row_stride = 8*512, x_seg_len = 8*512, x_seg_stride = 512*512, x_batch_stride = 8*512*512. */
+int mn_linear_small_m_ex(const float* x, long long x_row_stride, long long x_batch_stride, int x_seg_len, long long x_seg_stride,
+                         const float* w, const float* bias, const float* residual, long long res_batch_stride, float* y,
+                         int batches, int M, int K, int N, int act, float gain, void* stream);
+
 /* LayerNorm over the TOKEN axis followed by Linear(T -> To) over the token axis, i.e. the
  * `x.permute(0,2,1)` -> LayerNorm(T) -> Linear -> permute(0,2,1) idiom at
  * models/textvit_arch.py:154 (T=64 -> 16) and :72 (64 -> 1).  x:[B,T,D] -> out:[B,To,D]. */

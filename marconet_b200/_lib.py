@@ -5,7 +5,7 @@ resolved this module raises at import of the first operator, loudly.
 """
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_void_p
+from ctypes import c_longlong, POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmarconet_b200.so")
@@ -74,6 +74,8 @@ SYMBOLS = {
                                   c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "mn_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
     "mn_linear_small_m": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "mn_linear_small_m_ex": (c_int, [c_void_p, c_longlong, c_longlong, c_int, c_longlong, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p,
+                                     c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "mn_token_mix": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "mn_attention": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "mn_nchw_to_nhwc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),

@@ -1,5 +1,6 @@
 // TextViT helper operators (LayerNorm, token-axis LayerNorm+Linear, fused MHA) and NCHW<->NHWC
 // boundary conversion.  All fp32; these are latency/HBM-bound (S<=64 tokens, 512 features).
+#include <cstdlib>
 #include "mn_common.cuh"
 
 namespace {
@@ -95,39 +96,75 @@ __global__ void __launch_bounds__(256) attention_kernel(const float* __restrict_
     }
 }
 
-// Small-M linear layer (M <= 64 rows: the 64 / 16 tokens of one text line): y = act(x W + b + residual) * gain.
-// One block = all M rows x 16 output columns; K is streamed in 32-wide chunks through a 4-stage cp.async ring so that
-// four chunks of weights are in flight per block (the layer is pure HBM/L2 latency: 32..421 blocks, 2 KB of W per chunk).
-// No split-K, no second pass: the TextViT's ~45 GEMMs per line are launch/latency bound, not FLOP bound.
+// Small-M linear layer (M <= 64 rows: the 64 / 16 tokens of one text line, the 16 characters of the mapping network):
+//   y = act(x W + b + residual) * gain.
+// One CTA = MT rows (16/32/64, all of M) x NT output columns (16 or 64) x one K slice; K is streamed in 32-wide chunks through
+// a 4-stage cp.async ring.  These layers are pure latency / weight-streaming problems (a 512x512 layer is 1 MB of weights and
+// 0.03 GFLOP), so the work is spread over ~one CTA per SM: grid.y = ksplit K-slices that form ONE thread-block cluster; the
+// slices' partial sums are reduced through distributed shared memory in rank order (deterministic), and rank 0 runs the
+// epilogue.  x may be a gathered matrix: element (r, k) lives at x + r*x_rs + (k / seg_len)*seg_stride + k % seg_len, which is
+// how the TextViT patch embedding (Rearrange 'b c (h p1) (w p2) -> b h w (p1 p2 c)', textvit_arch.py:33-36) reads the NHWC
+// feature map in place.  grid.z = independent batches (lines).
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
     const int sz = valid ? 16 : 0;
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
 }
-__global__ void __launch_bounds__(128) linear_small_m_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                             const float* __restrict__ bias, const float* __restrict__ residual,
-                                                             float* __restrict__ y, int M, int K, int N, int act, float gain) {
+__device__ __forceinline__ uint32_t lin_cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void lin_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float lin_ld_peer(const float* my_smem_addr, uint32_t rank) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(my_smem_addr);
+    uint32_t pa; float v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(pa) : "r"(a), "r"(rank));
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(pa) : "memory");
+    return v;
+}
+
+struct LinArgs {
+    const float* x; long long x_rs, x_bs; int seg_len; long long seg_stride;
+    const float* w; const float* bias; const float* residual; long long res_bs;
+    float* y; int M, K, N, act; float gain;
+};
+
+template <int MT, int NT>
+__global__ void __launch_bounds__(128) linear_small_m_kernel(const LinArgs a) {
     mn_pdl_prologue();
-    constexpr int ST = 4;
-    __shared__ __align__(16) float Xs[ST][64][36];
-    __shared__ __align__(16) float Ws[ST][32][16];
+    constexpr int ST = 4, RPT = MT / 8, CPT = NT / 16, XLD = 36;
+    extern __shared__ __align__(16) float lin_smem[];
+    float (*Xs)[MT][XLD] = reinterpret_cast<float (*)[MT][XLD]>(lin_smem);
+    float (*Ws)[32][NT] = reinterpret_cast<float (*)[32][NT]>(lin_smem + ST * MT * XLD);
+    float (*red)[NT + 1] = reinterpret_cast<float (*)[NT + 1]>(lin_smem);          // reuses the ring after the K loop
     const int tid = threadIdx.x;
-    const int col = tid & 15, rg = tid >> 4;            // 16 columns x 8 row groups of 8 rows
-    const int n0 = blockIdx.x * 16;
-    float acc[8];
+    const int cg = tid & 15, rg = tid >> 4;              // 16 column groups x 8 row groups
+    const int n0 = blockIdx.x * NT;
+    const int ksplit = gridDim.y;
+    const uint32_t krank = ksplit > 1 ? lin_cluster_rank() : 0;
+    const float* xb = a.x + (size_t)blockIdx.z * a.x_bs;
+    const int nchunks_all = a.K / 32;
+    const int ch_begin = (int)((long long)nchunks_all * krank / ksplit), ch_end = (int)((long long)nchunks_all * (krank + 1) / ksplit);
+    const int nchunks = ch_end - ch_begin;
+    float acc[RPT][CPT];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    const int nchunks = K / 32;
+    for (int i = 0; i < RPT; ++i)
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) acc[i][c] = 0.f;
     auto issue = [&](int ch) {
         if (ch < nchunks) {
-            const int k0 = ch * 32, buf = ch % ST;
+            const int k0 = (ch_begin + ch) * 32, buf = ch % ST;
+            const float* xk = xb + (size_t)(k0 / a.seg_len) * a.seg_stride + (k0 % a.seg_len);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {               // X chunk: 64 rows x 32 floats = 512 x 16 B
+            for (int i = 0; i < MT / 16; ++i) {          // X chunk: MT rows x 32 floats
                 const int idx = tid + i * 128, r = idx >> 3, c4 = (idx & 7) * 4;
-                cp_async16(&Xs[buf][r][c4], x + (size_t)(r < M ? r : 0) * K + k0 + c4, r < M);
+                cp_async16(&Xs[buf][r][c4], xk + (size_t)(r < a.M ? r : 0) * a.x_rs + c4, r < a.M);
             }
-            const int kr = tid >> 2, c4 = (tid & 3) * 4; // W chunk: 32 rows x 16 floats = 128 x 16 B
-            cp_async16(&Ws[buf][kr][c4], w + (size_t)(k0 + kr) * N + n0 + c4, true);
+#pragma unroll
+            for (int i = 0; i < NT / 16; ++i) {          // W chunk: 32 rows x NT floats
+                const int idx = tid + i * 128, kr = idx / (NT / 4), c4 = (idx % (NT / 4)) * 4;
+                cp_async16(&Ws[buf][kr][c4], a.w + (size_t)(k0 + kr) * a.N + (n0 + c4 < a.N ? n0 + c4 : 0), n0 + c4 < a.N);
+            }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -140,27 +177,93 @@ __global__ void __launch_bounds__(128) linear_small_m_kernel(const float* __rest
         const int buf = ch % ST;
 #pragma unroll
         for (int k4 = 0; k4 < 8; ++k4) {
-            const float w0 = Ws[buf][k4 * 4][col], w1 = Ws[buf][k4 * 4 + 1][col], w2 = Ws[buf][k4 * 4 + 2][col], w3 = Ws[buf][k4 * 4 + 3][col];
+            float wv[4][CPT];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float4 xv = *reinterpret_cast<const float4*>(&Xs[buf][rg * 8 + i][k4 * 4]);
-                acc[i] = fmaf(xv.x, w0, acc[i]); acc[i] = fmaf(xv.y, w1, acc[i]);
-                acc[i] = fmaf(xv.z, w2, acc[i]); acc[i] = fmaf(xv.w, w3, acc[i]);
+            for (int kk = 0; kk < 4; ++kk) {
+                if constexpr (CPT == 4) {
+                    const float4 t = *reinterpret_cast<const float4*>(&Ws[buf][k4 * 4 + kk][cg * 4]);
+                    wv[kk][0] = t.x; wv[kk][1] = t.y; wv[kk][2] = t.z; wv[kk][3] = t.w;
+                } else {
+                    wv[kk][0] = Ws[buf][k4 * 4 + kk][cg];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) {
+                const float4 xv = *reinterpret_cast<const float4*>(&Xs[buf][rg * RPT + i][k4 * 4]);
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) {
+                    acc[i][c] = fmaf(xv.x, wv[0][c], acc[i][c]); acc[i][c] = fmaf(xv.y, wv[1][c], acc[i][c]);
+                    acc[i][c] = fmaf(xv.z, wv[2][c], acc[i][c]); acc[i][c] = fmaf(xv.w, wv[3][c], acc[i][c]);
+                }
             }
         }
         __syncthreads();
     }
-    const int o = n0 + col;
-    const float b = bias ? bias[o] : 0.f;
+    if (ksplit > 1) {
+        // K slices of one cluster: park the partials in shared memory, rank 0 adds them in rank order through DSMEM
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncthreads();
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int r = rg * 8 + i;
-        if (r < M) {
-            float v = acc[i] + b;
-            if (residual) v += residual[(size_t)r * N + o];
-            y[(size_t)r * N + o] = mn_apply_act(v, act) * gain;
+        for (int i = 0; i < RPT; ++i)
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) red[rg * RPT + i][cg * CPT + c] = acc[i][c];
+        lin_cluster_sync();
+        if (krank == 0) {
+            for (uint32_t q = 1; q < (uint32_t)ksplit; ++q)
+#pragma unroll
+                for (int i = 0; i < RPT; ++i)
+#pragma unroll
+                    for (int c = 0; c < CPT; ++c) acc[i][c] += lin_ld_peer(&red[rg * RPT + i][cg * CPT + c], q);
+        }
+        lin_cluster_sync();                              // peers keep their shared memory alive until rank 0 has read it
+        if (krank != 0) return;
+    }
+    float* yb = a.y + (size_t)blockIdx.z * a.M * a.N;
+    const float* rb = a.residual ? a.residual + (size_t)blockIdx.z * a.res_bs : nullptr;
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+        const int r = rg * RPT + i;
+        if (r >= a.M) continue;
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+            const int o = n0 + cg * CPT + c;
+            if (o >= a.N) continue;
+            float v = acc[i][c] + (a.bias ? a.bias[o] : 0.f);
+            if (rb) v += rb[(size_t)r * a.N + o];
+            yb[(size_t)r * a.N + o] = mn_apply_act(v, a.act) * a.gain;
         }
     }
+}
+
+template <int MT, int NT>
+static cudaError_t launch_linear(const LinArgs& a, int batches, int ksplit, cudaStream_t st) {
+    constexpr int ring = 4 * (MT * 36 + 32 * NT) * (int)sizeof(float), redb = MT * (NT + 1) * (int)sizeof(float);
+    constexpr int smem = ring > redb ? ring : redb;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(linear_small_m_kernel<MT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(mn_cdiv(a.N, NT), ksplit, batches);
+    cfg.blockDim = dim3(128, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (ksplit > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 1; attr[na].val.clusterDim.y = ksplit; attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (mn_pdl_enabled()) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr; cfg.numAttrs = na;
+    return cudaLaunchKernelEx(&cfg, linear_small_m_kernel<MT, NT>, a);
 }
 
 // 32x32 smem-tiled transposes between [C][HW] and [HW][C] per sample.
@@ -205,13 +308,41 @@ extern "C" int mn_layernorm(const float* x, float* y, const float* gamma, const 
     return MN_OK;
 }
 
-extern "C" int mn_linear_small_m(const float* x, const float* w, const float* bias, const float* residual, float* y,
-                                 int M, int K, int N, int act, float gain, void* stream) {
-    MN_REQUIRE(x && w && y && M > 0 && M <= 64 && K > 0 && K % 32 == 0 && N > 0 && N % 16 == 0, "mn_linear_small_m: needs M<=64, K%32==0, N%16==0");
+extern "C" int mn_linear_small_m_ex(const float* x, long long x_row_stride, long long x_batch_stride, int x_seg_len, long long x_seg_stride,
+                                    const float* w, const float* bias, const float* residual, long long res_batch_stride, float* y,
+                                    int batches, int M, int K, int N, int act, float gain, void* stream) {
+    MN_REQUIRE(x && w && y && M > 0 && M <= 64 && K > 0 && K % 32 == 0 && N > 0 && N % 16 == 0 && batches > 0 && batches <= 65535,
+               "mn_linear_small_m: needs M<=64, K%32==0, N%16==0");
     MN_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0, "mn_linear_small_m: x, w must be 16-byte aligned");
-    MN_CUDA_CHECK((mn_launch(linear_small_m_kernel, dim3(N / 16), dim3(128), 0, (cudaStream_t)stream, x, w, bias, residual, y, M, K, N, act, gain)));
+    MN_REQUIRE(x_seg_len > 0 && x_seg_len % 32 == 0 && K % x_seg_len == 0 && (x_row_stride & 3) == 0 && (x_seg_stride & 3) == 0 && (x_batch_stride & 3) == 0,
+               "mn_linear_small_m: gathered x needs 32-float segments and 16-byte aligned strides");
+    LinArgs a{x, x_row_stride, x_batch_stride, x_seg_len, x_seg_stride, w, bias, residual, res_batch_stride, y, M, K, N, act, gain};
+    // tile: all rows x 16 columns (many small CTAs: these layers are latency bound and 64-row x 64-column tiles leave too few
+    // warps per SM -- measured 39 vs 14 us for 64x512x1024); 64 columns only for the <= 16-row layers with many columns
+    // (the generator's 17 modulation FCs as one 16x512x7168 GEMM: 18 vs 30 us).
+    const bool wide = (M <= 16 && N >= 1024);
+    const int tiles = mn_cdiv(N, wide ? 64 : 16) * batches;
+    // K slices (one cluster, <= 8 CTAs): spread a small layer over ~one CTA per SM, a long K over ~two
+    const int sms = mn_num_sms(), chunks = K / 32;
+    const int budget = K >= 4096 ? 2 * sms : sms;
+    int ks = 1;
+    while (ks < 8 && tiles * ks * 2 <= budget && chunks / (ks * 2) >= 2) ks *= 2;
+    static int force_ks = -1;                            // developer override: MN_LIN_KS=1|2|4|8
+    if (force_ks < 0) { const char* e = getenv("MN_LIN_KS"); force_ks = e ? atoi(e) : 0; }
+    if (force_ks > 0) { ks = force_ks; while (ks > 1 && chunks / ks < 1) ks /= 2; }
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e;
+    const int mt = M <= 16 ? 16 : (M <= 32 ? 32 : 64);
+    if (wide) e = mt == 16 ? launch_linear<16, 64>(a, batches, ks, st) : (mt == 32 ? launch_linear<32, 64>(a, batches, ks, st) : launch_linear<64, 64>(a, batches, ks, st));
+    else e = mt == 16 ? launch_linear<16, 16>(a, batches, ks, st) : (mt == 32 ? launch_linear<32, 16>(a, batches, ks, st) : launch_linear<64, 16>(a, batches, ks, st));
+    MN_CUDA_CHECK(e);
     MN_LAUNCH_CHECK();
     return MN_OK;
+}
+
+extern "C" int mn_linear_small_m(const float* x, const float* w, const float* bias, const float* residual, float* y,
+                                 int M, int K, int N, int act, float gain, void* stream) {
+    return mn_linear_small_m_ex(x, K, 0, K, 0, w, bias, residual, 0, y, 1, M, K, N, act, gain, stream);
 }
 
 extern "C" int mn_token_mix(const float* x, const float* gamma, const float* beta, const float* w, const float* bias,

@@ -117,8 +117,11 @@ class TextViT(nn.Module):
         if s != 64:
             raise RuntimeError("TextViT is built for 32x512 LR lines (64 tokens)")
         pw, pb = pk["patch"]
-        x = ops.conv2d(feat, pw.w, 8, 8, stride=(8, 8), bias=pb, residual=pk["pe"].view(1, 1, s, -1), res_broadcast=True)
-        x = x.view(b * s, self.dim)
+        if b <= 4:      # weight-streaming GEMM with M = 64 tokens per line: gathered small-M kernel, K split over a cluster
+            x = ops.patch_embed(feat, pw.w, pb, pk["pe"])
+        else:
+            x = ops.conv2d(feat, pw.w, 8, 8, stride=(8, 8), bias=pb, residual=pk["pe"].view(1, 1, s, -1), res_broadcast=True)
+            x = x.view(b * s, self.dim)
         for blk in pk["layers"]:
             x = _block_run(blk, x, b, s)
         x_cls = _block_run(pk["cls"], x, b, s)

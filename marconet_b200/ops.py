@@ -210,6 +210,25 @@ def linear(x2d, w, bias=None, act=ACT_NONE, gain=1.0, residual=None, out=None, p
     return y.reshape(m, -1)
 
 
+def patch_embed(feat, w, bias, pe):
+    """TextViT patch embedding on the NHWC feature map in place (textvit_arch.py:33-36,68-69):
+    feat [B, 8, 8*T, C] -> tokens [B*T, D] = Linear(rearrange(feat, 'b (p1) (t p2) c -> b t (p1 p2 c)')) + pe[T, D].
+    ``w`` is the packed [8*8*C, D] weight (K order p1, p2, c)."""
+    global LAUNCHES
+    b, fh, fw, c, cs = nhwc_info(feat, "feat")
+    if fh != 8 or fw % 8 != 0 or cs != c:
+        raise RuntimeError("patch_embed: expects a dense [B, 8, 8*T, C] feature map")
+    t = fw // 8
+    k, d = w.shape
+    if k != 64 * c or t > 64 or tuple(pe.shape) != (t, d):
+        raise RuntimeError("patch_embed: weight / positional embedding do not match the feature map")
+    y = torch.empty((b * t, d), dtype=torch.float32, device=feat.device)
+    _lib.check(_lib.load().mn_linear_small_m_ex(_ptr(feat), 8 * c, 8 * fw * c, 8 * c, fw * c, _ptr(w), _ptr(bias), _ptr(pe), 0, _ptr(y),
+                                                b, t, k, d, ACT_NONE, 1.0, _stream()), "mn_linear_small_m_ex")
+    LAUNCHES += 1
+    return y
+
+
 def pixelnorm(x):
     global LAUNCHES
     _require_cuda(x, "x")

@@ -284,7 +284,8 @@ def test_layernorm_tokenmix_attention():
         _close(ops.attention(qkv.to(d)).cpu(), ref, 2e-5, f"attention S={s}")
 
 
-@pytest.mark.parametrize("m,k,n", [(64, 512, 512), (16, 512, 1536), (64, 1024, 512), (2, 512, 6736), (33, 64, 16)])
+@pytest.mark.parametrize("m,k,n", [(64, 512, 512), (16, 512, 1536), (64, 1024, 512), (2, 512, 6736), (33, 64, 16), (16, 512, 512),
+                                   (16, 512, 7168), (64, 512, 1024), (17, 4096, 1040), (32, 2048, 256)])
 def test_linear_small_m(m, k, n):
     from marconet_b200 import ops
     d = _dev()
@@ -293,6 +294,34 @@ def test_linear_small_m(m, k, n):
     _close(y.cpu(), F.gelu(x @ w + b + r) * 1.5, 2e-5, f"linear {m}x{k}x{n}")
     y = ops.linear(x.to(d), w.to(d))
     _close(y.cpu(), x @ w, 2e-5)
+
+
+def test_linear_small_m_is_deterministic():
+    """K slices are reduced through distributed shared memory in rank order: repeated launches give identical bits."""
+    from marconet_b200 import ops
+    d = _dev()
+    x, w = _rand(64, 512, seed=74).to(d), _rand(512, 512, seed=75, scale=512 ** -0.5).to(d)
+    first = ops.linear(x, w)
+    for _ in range(20):
+        assert torch.equal(ops.linear(x, w), first)
+
+
+@pytest.mark.parametrize("b", [1, 3])
+def test_patch_embed_gathered(b):
+    """TextViT patch embedding straight from the NHWC feature map (Rearrange + Linear + positional embedding)."""
+    from marconet_b200 import ops
+    d = _dev()
+    c, t, dim = 512, 64, 512
+    feat = _rand(b, 8, 8 * t, c, seed=80)                               # NHWC
+    w = _rand(64 * c, dim, seed=81, scale=(64 * c) ** -0.5)
+    bias, pe = _rand(dim, seed=82), _rand(t, dim, seed=83)
+    y = ops.patch_embed(feat.to(d), w.to(d), bias.to(d), pe.to(d))
+    tokens = feat.reshape(b, 8, t, 8, c).permute(0, 2, 1, 3, 4).reshape(b * t, 64 * c)     # (p1 p2 c) per token
+    ref = (tokens.double() @ w.double() + bias.double()).float() + pe.repeat(b, 1)
+    _close(y.cpu(), ref, 5e-5, "patch_embed")
+    conv = ops.conv2d(feat.to(d), w.to(d), 8, 8, stride=(8, 8), bias=bias.to(d), residual=pe.to(d).view(1, 1, t, -1), res_broadcast=True,
+                      precision=ops.PREC_FP32_SIMT)
+    _close(y.cpu(), conv.reshape(b * t, dim).cpu(), 5e-5, "patch_embed vs conv path")
 
 
 def test_layout_roundtrip():

@@ -65,6 +65,13 @@ def main():
         skip = torch.randn(n, h // 2, h // 2, 3, device=dev)
         add(f"torgb [{n},{h},{h},{c}]", lambda: ops.torgb(x, s, wt, b, skip), x.numel() * 4 + n * h * h * 3 * 4 * 1.25)
         del x
+    # small-M linears (weight streaming): bytes = the weight matrix
+    for m, k, n in ((16, 512, 512), (64, 512, 512), (64, 512, 1536), (64, 512, 1024), (64, 1024, 512), (64, 512, 6736), (16, 512, 7168)):
+        x, w, b = torch.randn(m, k, device=dev), torch.randn(k, n, device=dev), torch.randn(n, device=dev)
+        add(f"linear_small_m [{m}x{k}x{n}]", lambda: ops.linear(x, w, b), k * n * 4)
+    feat = torch.randn(1, 8, 512, 512, device=dev)
+    w, b, pe = torch.randn(32768, 512, device=dev), torch.randn(512, device=dev), torch.randn(64, 512, device=dev)
+    add("patch_embed [64x32768x512]", lambda: ops.patch_embed(feat, w, b, pe), 32768 * 512 * 4)
     # NCHW <-> NHWC and the final 64->3 conv are covered by bench_conv.py
     for r in rows:
         print(json.dumps(r))
