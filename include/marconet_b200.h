@@ -259,6 +259,23 @@ int mn_attention(const float* qkv, float* out, int B, int S, int heads, int dh, 
 int mn_nchw_to_nhwc(const float* x, float* y, int N, int C, int H, int W, int y_cs, void* stream);
 int mn_nhwc_to_nchw(const float* x, int x_cs, float* y, int N, int C, int H, int W, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Script pre/post-processing on the device (the reference does this on the host with cv2 / torchvision)
+ * ------------------------------------------------------------------------------------ */
+/* test_sr.py:98-111:  LQ = cv2.resize(img, (0,0), fx, fy, INTER_CUBIC)  (8-bit HWC image, OpenCV's own algorithm, bit-exact:
+ * see csrc/image_ops.cu), pasted into a zero out_h x out_w canvas, ToTensor, Normalize((.5,.5,.5),(.5,.5,.5)).
+ *   img:[h][w][cn] uint8 (device), dh = round_half_even(h*fy), dw = round_half_even(w*fx) (computed by the caller, as cv::resize
+ *   does), lq:[cn][out_h][out_w] fp32, lq_u8 (optional): the resized bytes [dh][dw][cn].  Fails when dw > out_w (the script skips
+ *   such images, test_sr.py:107-109). */
+int mn_preprocess_lq_u8(const uint8_t* img, int h, int w, int cn, double fx, double fy, int dh, int dw,
+                        float* lq, uint8_t* lq_u8, int out_h, int out_w, void* stream);
+
+/* test_sr.py:198-201 (+ the uint8 rounding of cv2.imwrite, :231):
+ *   out[b][y][x][C-1-c] = saturate_u8(round_half_even(clip(sr[b,c,y,x]*0.5 + 0.5, 0, 1) * 255)).
+ * sr is addressed through element strides so that the channels_last view the SR module returns is read in place. */
+int mn_postprocess_sr_u8(const float* sr, long long stride_n, long long stride_c, long long stride_h, long long stride_w,
+                         uint8_t* out, int B, int C, int H, int W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -499,3 +499,44 @@ def as_nhwc(x_nchw):
 def as_nchw_view(x_nhwc):
     """NHWC tensor -> NCHW-shaped view (channels_last strides); what the modules return."""
     return x_nhwc.permute(0, 3, 1, 2)
+
+
+# ---- script pre/post-processing on the device (SURVEY 8f n2) ---------------------------------------------------------
+def round_half_even(v):
+    """cv::saturate_cast<int>(double) = cvRound: round half to even (how cv::resize derives dsize from fx, fy)."""
+    return int(round(v))          # Python's round() is round-half-even on floats
+
+
+def preprocess_lq(img_u8, out_h=32, out_w=512, return_resized=False):
+    """test_sr.py:98-111 on the device.  img_u8: uint8 [h, w, 3] CUDA tensor (the BGR image the script reads) ->
+    (lq fp32 [1, 3, out_h, out_w], resized width).  Bit-identical to OpenCV's own INTER_CUBIC + ToTensor + Normalize."""
+    global LAUNCHES
+    if not isinstance(img_u8, torch.Tensor) or not img_u8.is_cuda:
+        raise RuntimeError("marconet_b200: img must be a CUDA tensor (there is no CPU path)")
+    if img_u8.dtype != torch.uint8 or img_u8.dim() != 3 or not img_u8.is_contiguous():
+        raise RuntimeError("preprocess_lq: expects a contiguous uint8 [h, w, c] image")
+    h, w, cn = img_u8.shape
+    fx = fy = out_h / h                                   # Python float division, like the script's fx=32/h
+    dh, dw = round_half_even(h * fy), round_half_even(w * fx)
+    if dw > out_w:
+        raise ValueError(f"LQ width {dw} exceeds {out_w}: crop the line into shorter segments (test_sr.py:107-109)")
+    lq = torch.empty((1, cn, out_h, out_w), dtype=torch.float32, device=img_u8.device)
+    small = torch.empty((dh, dw, cn), dtype=torch.uint8, device=img_u8.device) if return_resized else None
+    _lib.check(_lib.load().mn_preprocess_lq_u8(_ptr(img_u8), h, w, cn, fx, fy, dh, dw, _ptr(lq), _ptr(small), out_h, out_w, _stream()),
+               "mn_preprocess_lq_u8")
+    LAUNCHES += 1
+    return (lq, dw, small) if return_resized else (lq, dw)
+
+
+def postprocess_sr(sr):
+    """test_sr.py:198-201 (+ cv2.imwrite's rounding): fp32 [B, C, H, W] (any strides) -> uint8 [B, H, W, C], channels flipped."""
+    global LAUNCHES
+    _require_cuda(sr, "sr")
+    if sr.dtype != torch.float32 or sr.dim() != 4:
+        raise RuntimeError("postprocess_sr: expects an fp32 [B, C, H, W] tensor")
+    b, c, h, w = sr.shape
+    out = torch.empty((b, h, w, c), dtype=torch.uint8, device=sr.device)
+    sn, sc, sh, sw = sr.stride()
+    _lib.check(_lib.load().mn_postprocess_sr_u8(_ptr(sr), sn, sc, sh, sw, _ptr(out), b, c, h, w, _stream()), "mn_postprocess_sr_u8")
+    LAUNCHES += 1
+    return out

@@ -73,3 +73,39 @@ def restore_lines(encoder, tspgan, sr, lq, labels=None, locs=None, max_chars=16)
             priors.append(torch.zeros(0, 3, 128, 128, device=dev))
     out = sr(lq, p64, p32, locs)
     return dict(sr=out, prior=priors, labels=labels, locs=locs, w=w, logits=logits)
+
+
+def boxes_to_locs(boxes, h, lq_width=512):
+    """test_sr.py:118-134: detector boxes [x1, y1, x2, y2] in the ORIGINAL image -> locs [1, 2n] (centre, half-width) in units of
+    the LQ canvas width.  Python-float arithmetic exactly as the script, stored as fp32."""
+    locs = torch.zeros(1, len(boxes) * 2, dtype=torch.float32)
+    for i, box in enumerate(boxes):
+        x1, _, x2, _ = [float(v) for v in box]
+        center, width = (x1 + x2) / 2.0, (x2 - x1) / 2.0
+        locs[0, 2 * i] = (center * 32.0 / h) / lq_width
+        locs[0, 2 * i + 1] = (width * 32.0 / h) / lq_width
+    return locs
+
+
+@torch.no_grad()
+def restore_image(encoder, tspgan, sr, img_u8, labels, boxes):
+    """One text-line image end to end on the device (the body of test_sr.py's loop, :98-201, with the labels / boxes the
+    detector and OCR produced): uint8 [h, w, 3] image (host numpy / tensor or CUDA tensor) -> dict(sr_u8 [128, W, 3] uint8 bytes
+    as cv2.imwrite would store them, cropped to the line's width; sr fp32; lq; lq_width).
+    Pre- and post-processing run as CUDA kernels (mn_preprocess_lq_u8 / mn_postprocess_sr_u8)."""
+    from . import ops
+    dev = next(encoder.parameters()).device
+    img = torch.as_tensor(img_u8)
+    h = img.shape[0]
+    img = img.to(dev, non_blocking=True).contiguous()
+    lq, lq_w = ops.preprocess_lq(img)
+    locs = boxes_to_locs(boxes, h, lq.shape[-1]).to(dev)
+    _, _, w = encoder(lq)
+    lab = torch.as_tensor(labels, dtype=torch.long).reshape(-1, 1)
+    if lab.shape[0] == 0:
+        raise ValueError("no character labels (test_sr.py:160-162 skips such images)")
+    img_prior, f64, f32_ = tspgan(styles=w[:1].repeat(lab.shape[0], 1), labels=lab, noise=None)
+    out = sr(lq, [f64], [f32_], locs)
+    show_w = ops.round_half_even(img.shape[1] * (128 / h))    # ShowLQ = cv2.resize(img, fx=128/h, ...) (test_sr.py:98)
+    sr_u8 = ops.postprocess_sr(out)[0, :, :show_w]            # ShowSR = sr[:, :ShowLQ.shape[1]] (test_sr.py:201)
+    return dict(sr_u8=sr_u8, sr=out, lq=lq, lq_width=lq_w, prior=img_prior, locs=locs)
