@@ -52,7 +52,8 @@ class GraphedLines:
         torch.cuda.current_stream(device).wait_stream(side)
         torch.cuda.synchronize(device)
         l0 = ops.LAUNCHES
-        with torch.cuda.graph(self.graph), torch.no_grad():
+        # thread_local: other threads of the process (NCCL watchdog, NVML samplers) keep making CUDA calls during the capture
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"), torch.no_grad():
             self.outputs = self._step()
         self.launches = ops.LAUNCHES - l0
 
