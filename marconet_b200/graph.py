@@ -22,7 +22,7 @@ class GraphedLines:
 
     ``out`` (and everything in ``g.outputs``) is a static buffer that the next call overwrites."""
 
-    def __init__(self, encoder, tspgan, sr, lines=1, chars=16, height=32, width=512, device=None, warmup=2):
+    def __init__(self, encoder, tspgan, sr, lines=1, chars=16, height=32, width=512, device=None, warmup=2, overlap_trunk=True):
         if device is None:
             device = next(encoder.parameters()).device
         device = torch.device(device)
@@ -41,6 +41,12 @@ class GraphedLines:
         self.locs = locs.to(device)
         self.flag = torch.zeros((1,), dtype=torch.int32, device=device)
         self.outputs = None
+        # The SR decoder's LR trunk (networks.py:412-416) needs only the LR line: it is recorded on a second stream, as a parallel
+        # branch of the graph, beside the encoder and the first (small-grid, latency-bound) generator layers.  Its convolutions
+        # get their own split-K scratch so that the two branches never share one.
+        self.overlap_trunk = bool(overlap_trunk)
+        self._branch = torch.cuda.Stream(device=device) if self.overlap_trunk else None
+        self._trunk_ws = torch.empty(ops._WS_BYTES // 4, dtype=torch.float32, device=device) if self.overlap_trunk else None
         self.graph = torch.cuda.CUDAGraph()
         self.launches = 0
 
@@ -60,12 +66,22 @@ class GraphedLines:
     def _step(self):
         with ops.deferred_checks(self.flag):
             self.flag.zero_()
-            logits, locs_lr, w = self.encoder(self.lq)
+            trunk = None
+            if self.overlap_trunk:
+                main = torch.cuda.current_stream(self.device)
+                self._branch.wait_stream(main)
+                with torch.cuda.stream(self._branch), ops.use_workspace(self._trunk_ws):
+                    trunk = self.sr.trunk(self.lq)
+            # the encoder's classification / box branches also go to the second stream: the generator only waits for w
+            logits, locs_lr, w = self.encoder(self.lq, _branch=(self._branch, self._trunk_ws) if self.overlap_trunk else None)
             image, f64, f32_ = self.tspgan(styles=w.repeat_interleave(self.chars, dim=0), labels=self.labels, noise=None)
             n = self.chars
             p64 = [f64[b * n:(b + 1) * n] for b in range(self.lines)]
             p32 = [f32_[b * n:(b + 1) * n] for b in range(self.lines)]
-            out = self.sr(self.lq, p64, p32, self.locs)
+            if trunk is not None:
+                main.wait_stream(self._branch)                 # joins the trunk and the encoder's cls / box branches
+                trunk.record_stream(main)
+            out = self.sr(self.lq, p64, p32, self.locs, _trunk=trunk)
         return dict(sr=out, prior=image, fea64=f64, fea32=f32_, logits=logits, locs_lr=locs_lr, w=w)
 
     def load(self, lq=None, labels=None, locs=None):

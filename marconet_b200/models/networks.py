@@ -89,12 +89,13 @@ class TextContextEncoderV2(_PackedModule):
         return dict(resnet=self.resnet.pack(), vit=self.transformer.pack())
 
     @torch.no_grad()
-    def forward(self, lq):
+    def forward(self, lq, _branch=None):
+        """``_branch`` (stream, scratch): see TextViT.run -- logits / locs are produced on that stream and the caller joins it."""
         self._need_cuda(lq, "TextContextEncoderV2")
         pk = self._get_packed(lq.device)
         x = ops.nchw_to_nhwc(lq.float())
         feat = self.resnet.run(pk["resnet"], x)
-        return self.transformer.run(pk["vit"], feat)
+        return self.transformer.run(pk["vit"], feat, branch=_branch)
 
 
 # =========================================================================================
@@ -516,8 +517,35 @@ class TSPSRNet(_PackedModule):
             total += v.shape[0]
         return torch.as_strided(views[0], (total,) + tuple(views[0].shape[1:]), views[0].stride())
 
+    def _trunk(self, pk, lq):
+        """The LR trunk (reference networks.py:412-416): depends on the LR line only, not on the priors."""
+        dev, d = lq.device, self.dim
+        bsz = lq.shape[0]
+        x = ops.nchw_to_nhwc(lq.float())
+        h, w = x.shape[1], x.shape[2]
+        cat32 = torch.empty((bsz, h, w, d + d // 4), dtype=torch.float32, device=dev)        # [up(sq_f_16) | lq_f_32]
+        cat16 = torch.empty((bsz, h // 2, w // 2, d + d // 2), dtype=torch.float32, device=dev)  # [up(lq_f_8) | lq_f_16]
+        f32v, f16v = cat32[..., d:], cat16[..., d:]
+        ops.conv2d(x, pk["first_32"][0], 3, 3, pad=(1, 1), bias=pk["first_32"][1], act=ACT_LRELU02, out=f32v)
+        ops.conv2d(f32v, pk["first_16"][0], 3, 3, stride=(2, 2), pad=(1, 1), bias=pk["first_16"][1], act=ACT_LRELU02, out=f16v)
+        p8 = pk["conv_first_8"]
+        t = ops.conv2d(f16v, p8[0][0], 3, 3, stride=(2, 2), pad=(1, 1), bias=p8[0][1], act=ACT_LRELU02)
+        f8 = ops.conv2d(t, p8[1][0], 3, 3, pad=(1, 1), bias=p8[1][1])
+        ops.resample_modulate(f8, None, up=True, out=cat16[..., :d])
+        s16 = _two(pk["conv_body_16"], cat16)
+        ops.resample_modulate(s16, None, up=True, out=cat32[..., :d])
+        s32 = _two(pk["conv_body_32"], cat32)
+        return s32
+
     @torch.no_grad()
-    def forward(self, lq, priors64, priors32, locs):
+    def trunk(self, lq):
+        """Public handle on the LR trunk so that a pipeline can launch it early, on a second stream, while the encoder and the
+        prior generator run (it needs only the LR line): pass the result to forward(..., _trunk=...)."""
+        self._need_cuda(lq, "TSPSRNet")
+        return self._trunk(self._get_packed(lq.device), lq)
+
+    @torch.no_grad()
+    def forward(self, lq, priors64, priors32, locs, _trunk=None):
         self._need_cuda(lq, "TSPSRNet")
         dev = lq.device
         pk = self._get_packed(dev)
@@ -533,20 +561,7 @@ class TSPSRNet(_PackedModule):
         else:
             locs_host = locs.detach().to("cpu", torch.float32)
 
-        x = ops.nchw_to_nhwc(lq.float())
-        h, w = x.shape[1], x.shape[2]
-        cat32 = torch.empty((bsz, h, w, d + d // 4), dtype=torch.float32, device=dev)        # [up(sq_f_16) | lq_f_32]
-        cat16 = torch.empty((bsz, h // 2, w // 2, d + d // 2), dtype=torch.float32, device=dev)  # [up(lq_f_8) | lq_f_16]
-        f32v, f16v = cat32[..., d:], cat16[..., d:]
-        ops.conv2d(x, pk["first_32"][0], 3, 3, pad=(1, 1), bias=pk["first_32"][1], act=ACT_LRELU02, out=f32v)
-        ops.conv2d(f32v, pk["first_16"][0], 3, 3, stride=(2, 2), pad=(1, 1), bias=pk["first_16"][1], act=ACT_LRELU02, out=f16v)
-        p8 = pk["conv_first_8"]
-        t = ops.conv2d(f16v, p8[0][0], 3, 3, stride=(2, 2), pad=(1, 1), bias=p8[0][1], act=ACT_LRELU02)
-        f8 = ops.conv2d(t, p8[1][0], 3, 3, pad=(1, 1), bias=p8[1][1])
-        ops.resample_modulate(f8, None, up=True, out=cat16[..., :d])
-        s16 = _two(pk["conv_body_16"], cat16)
-        ops.resample_modulate(s16, None, up=True, out=cat32[..., :d])
-        s32 = _two(pk["conv_body_32"], cat32)
+        s32 = _trunk if _trunk is not None else self._trunk(pk, lq)
 
         if sum(counts) > 0:
             p32 = _two(pk["conv_32_to256"], self._gather_priors(priors32, 512, 32))

@@ -7,7 +7,6 @@ the input on the first block of a stage) -> ReLU; no BatchNorm, no biases.
 """
 import math
 
-import torch
 import torch.nn as nn
 
 from .. import ops
@@ -16,22 +15,9 @@ from ..ops import ACT_RELU
 _STAGES = ((32, 3, (2, 1)), (64, 4, (1, 1)), (128, 6, (2, 1)), (256, 6, (1, 1)), (512, 3, (1, 1)))
 
 
-_PADC = 64     # the tcgen05 conv kernels work on 64-channel blocks
-
-
-def _pack(w, pad_in=False, pad_out=False):
-    """[Cout, Cin, KH, KW] -> ops.ConvWeight.  ``pad_out`` / ``pad_in`` zero-pad a 32-channel side to 64 so that the 32-wide
-    stage of the net runs on the tensor-core kernels: its activations are kept as 64-channel NHWC buffers whose upper half is
-    exactly zero (zero weight columns write zeros, relu(0 + 0) = 0, zero weight rows ignore them)."""
-    w = w.detach()
+def _pack(w):
     cout, cin, kh, kw = w.shape
-    if pad_out and cout < _PADC:
-        w = torch.cat([w, w.new_zeros(_PADC - cout, cin, kh, kw)], dim=0)
-        cout = _PADC
-    if pad_in and cin < _PADC:
-        w = torch.cat([w, w.new_zeros(cout, _PADC - cin, kh, kw)], dim=1)
-        cin = _PADC
-    return ops.ConvWeight(w.permute(2, 3, 1, 0).reshape(kh * kw * cin, cout).contiguous(), kh * kw)
+    return ops.ConvWeight(w.detach().permute(2, 3, 1, 0).reshape(kh * kw * cin, cout).contiguous(), kh * kw)
 
 
 def conv1x1(in_planes, out_planes, stride=1):
@@ -53,13 +39,8 @@ class BasicBlock(nn.Module):
         self.stride = stride if isinstance(stride, tuple) else (stride, stride)
 
     def pack(self):
-        # stride-1 convs take the padded 64-channel buffer as it is (zero weight rows for the padding); strided convs run on
-        # the fp32 kernel and read only the real channels through a channel-slice view, so their K is not padded.
-        cin = self.conv1.in_channels
-        unit = self.stride == (1, 1)
-        return dict(c1=_pack(self.conv1.weight, pad_in=True, pad_out=True), c2=_pack(self.conv2.weight, pad_in=unit, pad_out=True),
-                    c2_in=self.conv2.in_channels, stride=self.stride, cin=cin,
-                    ds=None if self.downsample is None else _pack(self.downsample[0].weight, pad_in=unit, pad_out=True))
+        return dict(c1=_pack(self.conv1.weight), c2=_pack(self.conv2.weight), stride=self.stride,
+                    ds=None if self.downsample is None else _pack(self.downsample[0].weight))
 
 
 class ResNet(nn.Module):
@@ -86,21 +67,16 @@ class ResNet(nn.Module):
         blocks = []
         for li in range(1, 6):
             blocks += [b.pack() for b in getattr(self, f"layer{li}")]
-        return dict(stem=_pack(self.conv1.weight, pad_out=True), blocks=blocks)
+        return dict(stem=_pack(self.conv1.weight), blocks=blocks)
 
     @staticmethod
     def run(pk, x):
-        """x: NHWC [B,32,512,3] -> NHWC [B,8,512,512].  Activations of the 32-wide stage are 64-channel buffers with a zero
-        upper half (see _pack)."""
-        def real(t, c):          # the first c channels as a channel-slice view (x_cs stays 64): input of a strided conv
-            return t if t.shape[-1] == c else t[..., :c]
-
+        """x: NHWC [B,32,512,3] -> NHWC [B,8,512,512]."""
         x = ops.conv2d(x, pk["stem"], 3, 3, pad=(1, 1), act=ACT_RELU)
         for b in pk["blocks"]:
-            unit = b["stride"] == (1, 1)
             o = ops.conv2d(x, b["c1"], 1, 1, act=ACT_RELU)
-            r = x if b["ds"] is None else ops.conv2d(x if unit else real(x, b["cin"]), b["ds"], 1, 1, stride=b["stride"])
-            x = ops.conv2d(o if unit else real(o, b["c2_in"]), b["c2"], 3, 3, stride=b["stride"], pad=(1, 1), residual=r, act=ACT_RELU)
+            r = x if b["ds"] is None else ops.conv2d(x, b["ds"], 1, 1, stride=b["stride"])
+            x = ops.conv2d(o, b["c2"], 3, 3, stride=b["stride"], pad=(1, 1), residual=r, act=ACT_RELU)
         return x
 
     def forward(self, x):

@@ -108,8 +108,12 @@ class TextViT(nn.Module):
                   self.linear_w_maxlen[1].bias.detach().contiguous()),
         )
 
-    def run(self, pk, feat):
-        """feat: NHWC [B,8,512,512] -> (logits [B,64,6736], locs [B,32], w [B,512])."""
+    def run(self, pk, feat, branch=None):
+        """feat: NHWC [B,8,512,512] -> (logits [B,64,6736], locs [B,32], w [B,512]).
+
+        ``branch = (stream, split_k_scratch)``: the classification and box branches -- which the style vector ``w`` does not
+        depend on -- are launched on that stream, so that a pipeline that only waits for ``w`` (the prior generator) can go on
+        while they run.  The CALLER joins the stream (``main.wait_stream(stream)``) before it reads ``logits`` / ``locs``."""
         b, fh, fw, c = feat.shape
         if fh != 8 or fw % 8 != 0 or c != 512:
             raise RuntimeError(f"TextViT expects a [B,8,W,512] feature map, got {tuple(feat.shape)}")
@@ -124,21 +128,35 @@ class TextViT(nn.Module):
             x = x.view(b * s, self.dim)
         for blk in pk["layers"]:
             x = _block_run(blk, x, b, s)
-        x_cls = _block_run(pk["cls"], x, b, s)
-        (g, be), w16, b16 = pk["seq"]
-        x16 = ops.token_mix(x.view(b, s, -1), g, be, w16, b16)                     # [B,16,512]
-        x_loc = _block_run(pk["locs"], x16.view(b * 16, -1), b, 16)
-        x_w = _block_run(pk["w"], x, b, s)
 
-        ln, (w, bias) = pk["head_cls"]
-        logits = ops.linear(ops.layernorm(x_cls, *ln), w, bias).view(b, s, -1)
+        def cls_and_locs():
+            x_cls = _block_run(pk["cls"], x, b, s)
+            (g, be), w16, b16 = pk["seq"]
+            x16 = ops.token_mix(x.view(b, s, -1), g, be, w16, b16)                     # [B,16,512]
+            x_loc = _block_run(pk["locs"], x16.view(b * 16, -1), b, 16)
+            ln, (w, bias) = pk["head_cls"]
+            lg = ops.linear(ops.layernorm(x_cls, *ln), w, bias).view(b, s, -1)
+            ln, (w1, b1), (w2, b2) = pk["head_locs"]
+            hl = ops.linear(ops.layernorm(x_loc, *ln), w1, b1, act=ACT_GELU)
+            return lg, ops.linear(hl, w2, b2, act=ACT_SIGMOID).view(b, -1)
+
+        if branch is None:
+            logits, locs = cls_and_locs()
+        else:
+            stream, scratch = branch
+            main = torch.cuda.current_stream(feat.device)
+            stream.wait_stream(main)
+            x.record_stream(stream)
+            with torch.cuda.stream(stream), ops.use_workspace(scratch):
+                logits, locs = cls_and_locs()
+            logits.record_stream(main)
+            locs.record_stream(main)
+
+        x_w = _block_run(pk["w"], x, b, s)
         (g, be), w1, b1 = pk["wmax"]
         xw = ops.token_mix(x_w.view(b, s, -1), g, be, w1, b1).view(b, -1)          # [B,512]
         ln, (w, bias) = pk["head_w"]
         out_w = ops.linear(ops.layernorm(xw, *ln), w, bias)
-        ln, (w1, b1), (w2, b2) = pk["head_locs"]
-        hl = ops.linear(ops.layernorm(x_loc, *ln), w1, b1, act=ACT_GELU)
-        locs = ops.linear(hl, w2, b2, act=ACT_SIGMOID).view(b, -1)
         return logits, locs, out_w
 
     @torch.no_grad()

@@ -64,13 +64,38 @@ def nhwc_info(t, name="tensor"):
     return n, h, w, c, cs
 
 
+_WS_OVERRIDE = None
+
+
 def workspace(device):
+    """Split-K scratch of the conv kernels: one per device (single stream, like the reference scripts) unless a caller that runs
+    convolutions on a second stream installs its own with ``use_workspace``."""
+    if _WS_OVERRIDE is not None:
+        return _WS_OVERRIDE
     key = device.index if device.index is not None else torch.cuda.current_device()
     ws = _WS.get(key)
     if ws is None:
         ws = torch.empty(_WS_BYTES // 4, dtype=torch.float32, device=device)
         _WS[key] = ws
     return ws
+
+
+class use_workspace:
+    """Context manager: convolutions launched inside use ``ws`` (fp32 CUDA tensor) as their split-K scratch, so that they can run
+    on another stream concurrently with convolutions that use the per-device scratch."""
+
+    def __init__(self, ws):
+        self.ws, self.prev = ws, None
+
+    def __enter__(self):
+        global _WS_OVERRIDE
+        self.prev, _WS_OVERRIDE = _WS_OVERRIDE, self.ws
+        return self.ws
+
+    def __exit__(self, *exc):
+        global _WS_OVERRIDE
+        _WS_OVERRIDE = self.prev
+        return False
 
 
 class ConvWeight:
