@@ -69,3 +69,26 @@ def test_restore_lines_self_contained_flow(gpu_models, checkpoints):
     if same:
         osr = restate.tspsr_forward(checkpoints["sr"], lq, [o64], [o32], locs)
         assert (out["sr"].cpu() - osr).abs().max().item() <= 1e-3
+
+
+def test_boxes_to_locs_matches_the_script_arithmetic():
+    """test_sr.py:118-134 restated with the script's own statements (Python floats, stored into an fp32 tensor)."""
+    import torch
+    from marconet_b200 import pipeline
+    boxes = [[3.5, 2.0, 40.25, 30.0], [41.0, 1.0, 77.0, 31.0], [80.0, 0.0, 131.5, 33.0]]
+    h, lq_width = 37, 512
+    ref = torch.zeros(1, len(boxes) * 2).float()
+    for i, box in enumerate(boxes):
+        x1, y1, x2, y2 = box
+        center = (x1 + x2) / 2.0
+        width = (x2 - x1) / 2.0
+        center_norm = center * 32.0 / h
+        width_norm = width * 32.0 / h
+        ref[0, 2 * i] = center_norm / lq_width
+        ref[0, 2 * i + 1] = width_norm / lq_width
+    assert torch.equal(pipeline.boxes_to_locs(boxes, h, lq_width), ref)
+
+
+def test_round_half_even_is_cvround():
+    from marconet_b200 import ops
+    assert [ops.round_half_even(v) for v in (0.5, 1.5, 2.5, 2.4999, 186.45, 31.999999)] == [0, 2, 2, 2, 186, 32]
