@@ -66,22 +66,28 @@ class GraphedLines:
     def _step(self):
         with ops.deferred_checks(self.flag):
             self.flag.zero_()
-            trunk = None
+            trunk, trunk_done, branch = None, None, None
             if self.overlap_trunk:
+                branch = self._branch
                 main = torch.cuda.current_stream(self.device)
-                self._branch.wait_stream(main)
-                with torch.cuda.stream(self._branch), ops.use_workspace(self._trunk_ws):
+                branch.wait_stream(main)
+                with torch.cuda.stream(branch), ops.use_workspace(self._trunk_ws):
                     trunk = self.sr.trunk(self.lq)
-            # the encoder's classification / box branches also go to the second stream: the generator only waits for w
-            logits, locs_lr, w = self.encoder(self.lq, _branch=(self._branch, self._trunk_ws) if self.overlap_trunk else None)
-            image, f64, f32_ = self.tspgan(styles=w.repeat_interleave(self.chars, dim=0), labels=self.labels, noise=None)
+                    trunk_done = torch.cuda.Event()
+                    trunk_done.record(branch)
+            # the encoder's classification / box branches and the generator's ToRGB chain also go to the second stream: the
+            # generator only waits for w, the SR decoder only for the feature taps and the trunk
+            logits, locs_lr, w = self.encoder(self.lq, _branch=(branch, self._trunk_ws) if branch is not None else None)
+            image, f64, f32_ = self.tspgan(styles=w.repeat_interleave(self.chars, dim=0), labels=self.labels, noise=None, _branch=branch)
             n = self.chars
             p64 = [f64[b * n:(b + 1) * n] for b in range(self.lines)]
             p32 = [f32_[b * n:(b + 1) * n] for b in range(self.lines)]
             if trunk is not None:
-                main.wait_stream(self._branch)                 # joins the trunk and the encoder's cls / box branches
+                main.wait_event(trunk_done)
                 trunk.record_stream(main)
             out = self.sr(self.lq, p64, p32, self.locs, _trunk=trunk)
+            if branch is not None:
+                main.wait_stream(branch)                       # joins logits / locs and the prior image
         return dict(sr=out, prior=image, fea64=f64, fea32=f32_, logits=logits, locs_lr=locs_lr, w=w)
 
     def load(self, lq=None, labels=None, locs=None):

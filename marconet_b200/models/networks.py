@@ -243,7 +243,9 @@ class TextGenerator(_PackedModule):
 
     # ---- forward --------------------------------------------------------------------------
     @torch.no_grad()
-    def forward(self, styles, labels, noise=None):
+    def forward(self, styles, labels, noise=None, _branch=None):
+        """``_branch``: a second CUDA stream for the ToRGB chain (the 128-px prior image), which the feature taps -- and hence the
+        SR decoder -- do not depend on; the CALLER joins that stream before it reads the image."""
         self._need_cuda(styles, "TSPGAN")
         dev = styles.device
         pk = self._get_packed(dev)
@@ -283,17 +285,28 @@ class TextGenerator(_PackedModule):
             return ops.conv2d(x, e["w"], 3, 3, pad=(1, 1), bias=e["bias"], out_scale=demods[i], act=ACT_LRELU02,
                               gain=SQRT2, want_y=want_y, out2=(True if next_i is not None else None), y2_scale=y2s)
 
+        main = torch.cuda.current_stream(dev) if _branch is not None else None
+
+        def rgb(y, r, skip):
+            if _branch is None:
+                return ops.torgb(y, s_of(r), r["w"], r["bias"], skip)
+            _branch.wait_stream(main)                               # y (and s_all) are ready on the main stream
+            y.record_stream(_branch)
+            with torch.cuda.stream(_branch):
+                out = ops.torgb(y, s_of(r), r["w"], r["bias"], skip)
+            out.record_stream(main)
+            return out
+
         x = ops.select_text(pk["emb"], lab_dev, s_of(st[0]), n, l)   # embedding * style(conv1)
         y = styled(0, x, True)
-        skip = ops.torgb(y, s_of(pk["rgb"][0]), pk["rgb"][0]["w"], pk["rgb"][0]["bias"], None)
+        skip = rgb(y, pk["rgb"][0], None)
         taps = {}
         for j in range(len(self.to_rgbs)):
             ia, ib = 1 + 2 * j, 2 + 2 * j
             xu = ops.resample_modulate(y, s_of(st[ia]), up=True)     # bilinear x2 of the un-modulated map, then style
             xm = styled(ia, xu, False, next_i=ib)                    # only the pre-modulated operand of conv b is kept
             y = styled(ib, xm, True)
-            r = pk["rgb"][1 + j]
-            skip = ops.torgb(y, s_of(r), r["w"], r["bias"], skip)
+            skip = rgb(y, pk["rgb"][1 + j], skip)
             taps[y.shape[1]] = y
         return ops.as_nchw_view(skip), ops.as_nchw_view(taps[64]), ops.as_nchw_view(taps[32])
 
@@ -303,8 +316,8 @@ class TSPGAN(nn.Module):
         super().__init__()
         self.TextGenerator = TextGenerator(size=out_size, style_dim=num_style_feat, n_mlp=num_mlp, class_num=class_num)
 
-    def forward(self, styles, labels, noise):
-        return self.TextGenerator(styles, labels, noise)
+    def forward(self, styles, labels, noise, _branch=None):
+        return self.TextGenerator(styles, labels, noise, _branch=_branch)
 
 
 # =========================================================================================
