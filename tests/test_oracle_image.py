@@ -66,3 +66,23 @@ def test_postprocess_bytes():
     ref = np.clip((sr * np.float32(0.5) + np.float32(0.5)).transpose(0, 2, 3, 1)[..., ::-1], 0, 1) * np.float32(255.0)
     assert np.array_equal(out, np.rint(ref).astype(np.uint8))
     assert out[0, 0, 0, 2] == 0 and out[0, 0, 1, 2] == 255       # channel 0 lands in the last byte (flip)
+
+
+def test_oracle_reproduces_the_reference_script_png_row(checkpoints):
+    """uint8 image -> oracle pre-processing -> oracle nets -> oracle post-processing equals, byte for byte, the SR row of the PNG
+    the UNMODIFIED reference test_sr.py wrote on the CPU (tests/golden/script_sr_row.npz, oracle/make_golden_script.py)."""
+    import torch
+    from marconet_b200 import pipeline
+    from oracle import image_ops, restate
+    g = np.load(os.path.join(os.path.dirname(GOLDEN), "script_sr_row.npz"))
+    img, boxes, labels, stride = g["image_rgb"], g["boxes"], g["labels"], int(g["stride"])
+    lq, lq_w = image_ops.preprocess_lq(img)
+    assert lq_w == 256
+    lq_t = torch.from_numpy(lq)
+    locs = pipeline.boxes_to_locs(boxes.tolist(), img.shape[0], 512)
+    _, _, w = restate.encoder_forward(checkpoints["encoder"], lq_t)
+    lab = torch.from_numpy(labels).reshape(-1, 1)
+    _, f64, f32_ = restate.tspgan_forward(checkpoints["tspgan"], w[:1].repeat(lab.shape[0], 1), lab)
+    sr = restate.tspsr_forward(checkpoints["sr"], lq_t, [f64], [f32_], locs)
+    row = image_ops.postprocess_sr(sr.numpy())[0, :, :1024]
+    assert np.array_equal(row[::stride, ::stride], g["sr_row"])
