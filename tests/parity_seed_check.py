@@ -1,4 +1,5 @@
-"""Ad-hoc parity check of the whole path on a different synthetic checkpoint / input seed than the committed fixtures."""
+"""Ad-hoc parity check of the whole path on a different synthetic checkpoint / input seed than the committed fixtures
+(a script, not collected by pytest: python tests/parity_seed_check.py SEED NCHARS).  Lives under tests/ because it runs the oracle."""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
