@@ -89,3 +89,46 @@ def test_char_windows_ownership_last_writer_wins():
     assert owner[0][90] == 0 and owner[0][100] == 1 and owner[0][120] == 1 and owner[0][5] == 2 and owner[0][200] == -1
     with pytest.raises(RuntimeError):
         char_windows(torch.tensor([[-0.2, 0.0]]), [1], 512, 16)
+
+
+def test_char_windows_match_a_literal_restatement_on_random_boxes():
+    """Window integers (INT parity): the host function against the reference's statements executed literally with
+    0-dim torch tensors (networks.py:426-441 for the 32-row level, :460-474 for the 64-row level), on random and adversarial
+    centres (products that land within one ulp of an integer, the clipped ends)."""
+    import torch
+    from marconet_b200.models.networks import char_windows
+    g = torch.Generator().manual_seed(123)
+    for width, half in ((512, 16), (1024, 32)):
+        centres = [torch.rand(64, generator=g)]
+        k = torch.arange(1, 65, dtype=torch.float32) * 7
+        centres += [k / width, torch.nextafter(k / width, torch.tensor(0.0)), torch.nextafter(k / width, torch.tensor(2.0))]
+        centres.append(torch.tensor([0.0, 1.0, 15.999 / width, 16.0 / width, (width - 16.0) / width, (width - 15.999) / width] + [0.5] * 58))
+        locs = torch.zeros(len(centres), 128)
+        for b, c in enumerate(centres):
+            locs[b, 0::2] = c
+        counts = [64] * len(centres)
+        wins, valid, owner = char_windows(locs, counts, width, half)
+        i = 0
+        for b in range(len(centres)):
+            for c in range(64):
+                center = (locs[b][2 * c] * width).int()
+                wd = half
+                if center < wd:
+                    x1 = 0
+                else:
+                    x1 = center - wd
+                if center + wd > width:
+                    x2 = width
+                else:
+                    x2 = center + wd
+                y1 = half - torch.div(x2 - x1, 2, rounding_mode='trunc')
+                assert wins[i] == (b, int(x1), int(x2), int(y1)) and valid[i] == int(x2 - x1), (width, b, c, wins[i])
+                i += 1
+        # ownership: the last character in program order whose window covers the column
+        for b in range(len(centres)):
+            expect = [-1] * width
+            for c in range(64):
+                _, x1, x2, _ = wins[b * 64 + c]
+                for x in range(x1, x2):
+                    expect[x] = b * 64 + c
+            assert owner[b] == expect
