@@ -305,6 +305,29 @@ def run_ours(args):
 
         roof = modconv_roofline(nets["tspgan"], chars, dev) if rank == 0 else None
 
+        # informational: end to end through GraphedLines (this repo's own extension API) with the same host buffers and copies.
+        # Single process only (no collectives inside, so a failure here cannot desynchronise ranks); runs last.
+        if world == 1 and g is not None and graph_info and "ms_per_step" in graph_info:
+            try:
+                def e2e_graph_step():
+                    out = g(lq_pin, None, locs_pin)            # H2D into the static buffers + one graph replay
+                    sr_host.copy_(out, non_blocking=True)
+                    torch.cuda.current_stream().synchronize()
+
+                e2e_graph_step()
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                ev0.record()
+                for _ in range(args.steps):
+                    e2e_graph_step()
+                ev1.record()
+                torch.cuda.synchronize()
+                g.check()
+                graph_info["e2e_ms_per_step"] = ev0.elapsed_time(ev1) / args.steps
+                graph_info["e2e_chars_per_sec"] = lines * chars / (graph_info["e2e_ms_per_step"] / 1e3)
+            except Exception as exc:
+                graph_info["e2e_error"] = f"{type(exc).__name__}: {exc}"[:200]
+
     total_chars = world * lines * chars
     ms_step = ms_total / args.steps
     ms_eager = ms_step
