@@ -321,11 +321,8 @@ TcPlan plan_tc(const ConvGeom& g) {
 template <int NT, int STAGES>
 int launch_tc(const CUtensorMap& ma, const CUtensorMap& mbh, const CUtensorMap& mbl, const ConvGeom& g, const TcGeom& t, cudaStream_t st) {
     constexpr int SMEM = STAGES * (A_BYTES + 2 * NT * 128) + 1024 + 256;
-    static bool attr = false;
-    if (!attr) {
-        MN_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<NT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-        attr = true;
-    }
+    static unsigned long long smem_done = 0;
+    MN_CUDA_CHECK(mn_ensure_dyn_smem(conv_tc_kernel<NT, STAGES>, SMEM, &smem_done));
     dim3 grid(t.tiles_w * t.tiles_h * t.tiles_n, g.Cout / NT);
     conv_tc_kernel<NT, STAGES><<<grid, NUM_THREADS, SMEM, st>>>(ma, mbh, mbl, g, t);
     MN_LAUNCH_CHECK();

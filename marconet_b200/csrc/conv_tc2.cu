@@ -534,11 +534,8 @@ Tc2Plan plan_tc2(const ConvGeom& g) {
 
 template <int NT, bool GN>
 int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mbh, const CUtensorMap& mbl, const ConvGeom& g, const Tc2Plan& p, cudaStream_t st) {
-    static int smem_set = 0;
-    if (smem_set < p.smem) {
-        MN_CUDA_CHECK(cudaFuncSetAttribute(conv_tc2_kernel<NT, GN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-        smem_set = SMEM_LIMIT;
-    }
+    static unsigned long long smem_done = 0;
+    MN_CUDA_CHECK(mn_ensure_dyn_smem(conv_tc2_kernel<NT, GN>, SMEM_LIMIT, &smem_done));
     const Tc2Geom& t = p.t;
     const int total_work = t.m_groups * t.n_tiles * t.ksplit;
     int sms = mn_num_sms();

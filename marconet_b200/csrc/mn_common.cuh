@@ -76,5 +76,18 @@ static inline cudaError_t mn_launch(void (*kernel)(KArgs...), dim3 grid, dim3 bl
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of a kernel: raise it once per (kernel, device), so that one
+// process may drive several GPUs.  `done_mask` is a function-local static of the caller (bit d = done on device d).
+template <typename F>
+static inline cudaError_t mn_ensure_dyn_smem(F* kernel, int bytes, unsigned long long* done_mask) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64 && ((*done_mask >> dev) & 1ull)) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess && dev >= 0 && dev < 64) *done_mask |= 1ull << dev;
+    return e;
+}
+
 int mn_num_sms();
 int mn_max_ctas();   // 0 = use every SM; >0 = cap for persistent kernels (leaves SMs to concurrent NCCL kernels)

@@ -239,11 +239,10 @@ template <int MT, int NT>
 static cudaError_t launch_linear(const LinArgs& a, int batches, int ksplit, cudaStream_t st) {
     constexpr int ring = 4 * (MT * 36 + 32 * NT) * (int)sizeof(float), redb = MT * (NT + 1) * (int)sizeof(float);
     constexpr int smem = ring > redb ? ring : redb;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(linear_small_m_kernel<MT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    static unsigned long long smem_done = 0;
+    {
+        cudaError_t e = mn_ensure_dyn_smem(linear_small_m_kernel<MT, NT>, smem, &smem_done);
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(mn_cdiv(a.N, NT), ksplit, batches);
@@ -357,11 +356,8 @@ extern "C" int mn_attention(const float* qkv, float* out, int B, int S, int head
     MN_REQUIRE(qkv && out && B > 0 && heads > 0, "mn_attention: bad args");
     MN_REQUIRE(S > 0 && S <= 64 && dh == 64, "mn_attention: needs S<=64 and dh==64 (got S=%d dh=%d)", S, dh);
     constexpr int kSmem = (64 * 64 * 2 + 64 * 65 * 2) * (int)sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        MN_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-        attr_set = true;
-    }
+    static unsigned long long smem_done = 0;
+    MN_CUDA_CHECK(mn_ensure_dyn_smem(attention_kernel, kSmem, &smem_done));
     MN_CUDA_CHECK((mn_launch(attention_kernel, dim3(B * heads), dim3(256), kSmem, (cudaStream_t)stream, qkv, out, S, heads, scale)));
     MN_LAUNCH_CHECK();
     return MN_OK;
