@@ -25,6 +25,47 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert lib.mn_version() >= 100
 
 
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Every prototype of include/marconet_b200.h against its ctypes binding: argument count and argument class (pointer /
+    int / long long / float / double) and the return type -- a wrong binding would otherwise only show up on the GPU box."""
+    from marconet_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "marconet_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    protos = re.findall(r"(?m)^\s*(const char\s*\*|int64_t|int)\s+(mn_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header)
+    assert len(protos) >= 30
+
+    def klass(decl):
+        decl = decl.strip()
+        if decl == "void":
+            return None
+        if "*" in decl:
+            return "ptr"
+        if re.search(r"\blong long\b|\bint64_t\b", decl):
+            return "i64"
+        if re.search(r"\bdouble\b", decl):
+            return "f64"
+        if re.search(r"\bfloat\b", decl):
+            return "f32"
+        if re.search(r"\b(int|int32_t|unsigned)\b", decl):
+            return "i32"
+        raise AssertionError(f"unparsed parameter {decl!r}")
+
+    def cklass(t):
+        if t in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(t, "contents") or (isinstance(t, type) and issubclass(t, ctypes._Pointer)):
+            return "ptr"
+        return {ctypes.c_int: "i32", ctypes.c_int32: "i32", ctypes.c_longlong: "i64", ctypes.c_int64: "i64", ctypes.c_float: "f32",
+                ctypes.c_double: "f64"}[t]
+
+    seen = set()
+    for ret, name, params in protos:
+        want = [k for k in (klass(p) for p in params.split(",")) if k is not None]
+        restype, argtypes = _lib.SYMBOLS[name]
+        assert [cklass(t) for t in argtypes] == want, f"{name}: header {want} vs ctypes {[cklass(t) for t in argtypes]}"
+        assert restype is {"int": ctypes.c_int, "int64_t": ctypes.c_int64}.get(ret, ctypes.c_char_p), name
+        seen.add(name)
+    assert seen == set(_lib.SYMBOLS), sorted(set(_lib.SYMBOLS) ^ seen)
+
+
 def test_conv_params_struct_matches_header_field_order():
     from marconet_b200 import _lib
     header = open(os.path.join(ROOT, "include", "marconet_b200.h")).read()
