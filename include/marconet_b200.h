@@ -105,6 +105,16 @@ typedef struct {
     const float* gn_mean_rstd;                 /* [N][Cin/32][2] from mn_groupnorm_stats, or NULL                          */
     const float* gn_gamma; const float* gn_beta;   /* [Cin]                                                                */
     int gn_swish;
+    /* fp16-range management of the tensor-core precisions (the fp16 hi/lo split needs |x * x_scale| < 65504; the reference
+     * computes in fp32, models/networks.py:294,299 / F.conv2d everywhere, and has no such limit):
+     *   x_scale   power of two applied to the A operand before it is split and undone exactly in the epilogue (0 -> 1);
+     *   x_absmax  optional DEVICE float: atomic max of |x * x_scale| over every element the kernel consumed (calibration);
+     *   range_flag optional int32 the kernel STORES range_tag into when an operand element left the representable range
+     *             (fp16 modes: |x * x_scale| >= 65504; every mode: Inf / NaN).  May point to pinned host memory (plain store). */
+    float x_scale;
+    float* x_absmax;
+    int32_t* range_flag;
+    int32_t range_tag;
 } mn_conv_params;
 
 int mn_conv2d_nhwc(const mn_conv_params* p, void* stream);
@@ -218,6 +228,16 @@ int mn_window_scatter(const float* feat, int feat_cs, const float* scale, const 
  *   becomes a zero-width window. */
 int mn_char_windows(const float* locs, int locs_stride, const int32_t* line_first, int B, int max_chars, int W, int half,
                     mn_window* win, int32_t* valid, int32_t* owner, int32_t* err, void* stream);
+
+/* The reference module's standalone helper functions on NCHW-contiguous tensors (rows = B*C, len = H*W); the hot path uses
+ * the fused NHWC kernels above.
+ *   mn_swish         x * sigmoid(x)                                                models/networks.py:492-493
+ *   mn_row_mean_std  mean, sqrt(unbiased var + eps) of every row                   calc_mean_std_4D, :518-525
+ *   mn_adain_rows    (prior - prior_mean)/prior_std * lq_std + lq_mean per row     adaptive_instance_normalization, :528-533 */
+int mn_swish(const float* x, float* y, long long n, void* stream);
+int mn_row_mean_std(const float* x, float* mean, float* stdv, int rows, int len, float eps, void* stream);
+int mn_adain_rows(const float* prior, const float* prior_mean, const float* prior_std, const float* lq_mean,
+                  const float* lq_std, float* out, int rows, int len, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * TextViT operators

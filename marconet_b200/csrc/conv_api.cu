@@ -37,6 +37,7 @@ static int make_geom(const mn_conv_params* p, ConvGeom& g) {
     MN_REQUIRE(M < (1ll << 31) && (int64_t)p->KH * p->KW * p->Cin < (1ll << 31), "mn_conv2d_nhwc: problem too large");
     g.M = (int)M; g.K = p->KH * p->KW * p->Cin;
     g.ktiles = g.ktiles_per_split = 0; g.splits = 1;
+    g.x_scale = p->x_scale > 0.f ? p->x_scale : 1.f; g.x_absmax = p->x_absmax; g.range_flag = p->range_flag; g.range_tag = p->range_tag;
     return MN_OK;
 }
 

@@ -14,7 +14,19 @@ struct ConvGeom {
     int act; float gain;
     int M, K;
     int ktiles, ktiles_per_split, splits;
+    float x_scale; float* x_absmax; int32_t* range_flag; int32_t range_tag;   // fp16-range management (tensor-core precisions)
 };
+
+// Range bookkeeping of the operand-split stage: `amax` is the running max of (bits(|x * x_scale|)) a thread has seen.
+__device__ __forceinline__ void conv_range_report(const ConvGeom& g, uint32_t amax, bool fp16_mode) {
+    if (!g.x_absmax && !g.range_flag) return;
+    amax = __reduce_max_sync(0xffffffffu, amax);
+    if ((threadIdx.x & 31) == 0) {
+        if (g.x_absmax) atomicMax(reinterpret_cast<unsigned int*>(g.x_absmax), amax);
+        // 65504 = 0x477FE000; Inf / NaN >= 0x7F800000
+        if (g.range_flag && amax >= (fp16_mode ? 0x477FE000u : 0x7F800000u)) *reinterpret_cast<volatile int32_t*>(g.range_flag) = g.range_tag;
+    }
+}
 
 // Epilogue for 4 consecutive output channels [o, o+4) of GEMM row m (pixel index in [N,OH,OW]).
 //   v = acc*out_scale[n][o] + bias[o] + residual ; v = act(v)*gain ; masked by valid_w ; y, y2 stores.

@@ -152,6 +152,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
         const bool bf = t.prec == MN_PREC_BF16X3_TC;
         const uint32_t mask = bf ? 0xFFFF0000u : 0xFFFFE000u;
+        const float xs = g.x_scale;
+        uint32_t amax = 0;                     // range guard, see conv_common.cuh
         for (int kb = 0; kb < num_kb; ++kb) {
             const int s = kb % STAGES;
             const uint32_t ph = (kb / STAGES) & 1;
@@ -162,7 +164,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int box = 0; box < 2; ++box) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float4 v = *reinterpret_cast<const float4*>(a_src + box * A_BOX_BYTES + ((j ^ (r & 7)) << 4));
+                    float4 v = *reinterpret_cast<const float4*>(a_src + box * A_BOX_BYTES + ((j ^ (r & 7)) << 4));
+                    v.x *= xs; v.y *= xs; v.z *= xs; v.w *= xs;
+                    amax = max(max(amax, __float_as_uint(v.x) & 0x7FFFFFFFu), max(__float_as_uint(v.y) & 0x7FFFFFFFu,
+                               max(__float_as_uint(v.z) & 0x7FFFFFFFu, __float_as_uint(v.w) & 0x7FFFFFFFu)));
                     const float h0 = __uint_as_float(__float_as_uint(v.x) & mask), h1 = __uint_as_float(__float_as_uint(v.y) & mask);
                     const float h2 = __uint_as_float(__float_as_uint(v.z) & mask), h3 = __uint_as_float(__float_as_uint(v.w) & mask);
                     const int c = box * 16 + j * 2;
@@ -185,6 +190,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_arrive(bar_conv(s));
         }
 
+        conv_range_report(g, amax, t.prec == MN_PREC_F16X3_TC || t.prec == MN_PREC_F16X1_TC);
         // ---- epilogue ----
         mbar_wait(bar_acc, 0);
         tc_fence_after();
@@ -194,7 +200,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int n = n0 + tn, oy = oy0 + th, ox = ox0 + tw;
         const bool row_ok = n < g.N && oy < g.OH && ox < g.OW;
         const int m = (n * g.OH + oy) * g.OW + ox;
-        const float wscale = t.wscale ? *t.wscale : 1.f;
+        const float wscale = (t.wscale ? *t.wscale : 1.f) / g.x_scale;
         const float dfix = 1.f + 1.5e-8f * (float)(num_kb * (KB / 16));   // expected truncation shrink of the main accumulator, see conv_tc2.cu
 #pragma unroll 1
         for (int chunk = 0; chunk < NT / 16; ++chunk) {

@@ -180,7 +180,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int q = warp & 3;
         const int r = q * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-        const float wscale = t.wscale ? *t.wscale : 1.f;
+        const float wscale = (t.wscale ? *t.wscale : 1.f) / g.x_scale;      // x_scale is a power of two: exact
+        const float xs = g.x_scale;
+        uint32_t amax = 0;                                                  // max |x * x_scale| bits this thread has split (range guard)
         // The tensor core truncates (toward zero) every time it adds into the fp32 accumulator: measured mean shrink of the
         // main accumulator = 1.56e-8 per accumulation step, sign-symmetric, independent of K (tools/probe_tc_bias.py).  Undo the
         // expected shrink of D (K/16 steps); Dc is 2^-11 of the result and needs nothing.
@@ -328,6 +330,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                 }
                                 v = make_float4(tt[0], tt[1], tt[2], tt[3]);
                             }
+                            v.x *= xs; v.y *= xs; v.z *= xs; v.w *= xs;
+                            amax = max(max(amax, __float_as_uint(v.x) & 0x7FFFFFFFu), max(__float_as_uint(v.y) & 0x7FFFFFFFu,
+                                       max(__float_as_uint(v.z) & 0x7FFFFFFFu, __float_as_uint(v.w) & 0x7FFFFFFFu)));
                             const float h0 = __uint_as_float(__float_as_uint(v.x) & mask), h1 = __uint_as_float(__float_as_uint(v.y) & mask);
                             const float h2 = __uint_as_float(__float_as_uint(v.z) & mask), h3 = __uint_as_float(__float_as_uint(v.w) & mask);
                             const int c = box * 16 + j * 2;
@@ -355,6 +360,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             prev_work = work;
         }
         if (prev_work >= 0) epilogue(prev_work);
+        conv_range_report(g, amax, t.prec == MN_PREC_F16X3_TC || t.prec == MN_PREC_F16X1_TC);
     } else if (warp == 1) {
         // =========================== MMA issuer (whole warp converged, one elected lane issues) ===========================
         const uint32_t fmt = (t.prec == MN_PREC_BF16X3_TC) ? 1u : 0u;

@@ -304,7 +304,77 @@ __global__ void char_windows_kernel(const float* __restrict__ locs, int locs_str
     }
 }
 
+// ---------------------------------------------------------------- standalone helper functions of the reference module
+// swish (networks.py:492-493), calc_mean_std_4D (:518-525), adaptive_instance_normalization (:528-533) on NCHW-contiguous
+// tensors, rows = B*C, len = H*W.  The hot path uses the fused NHWC kernels above; these keep the reference's module-level
+// function names usable on CUDA tensors.
+__global__ void swish_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n) {
+    mn_pdl_prologue();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = x[i];
+        y[i] = v * (1.f / (1.f + expf(-v)));
+    }
+}
+
+// one block per row: mean and sqrt(unbiased variance + eps); two-pass in fp64 partials (matches torch.var to fp32 rounding)
+__global__ void row_mean_std_kernel(const float* __restrict__ x, float* __restrict__ mean, float* __restrict__ stdv, int len, float eps) {
+    mn_pdl_prologue();
+    __shared__ double red[32];
+    __shared__ double s_mean;
+    const float* xr = x + (size_t)blockIdx.x * len;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    double a = 0.0;
+    for (int i = threadIdx.x; i < len; i += blockDim.x) a += (double)xr[i];
+    a = mn_warp_sum_d(a);
+    if (lane == 0) red[warp] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) { double t = 0.0; for (int w = 0; w < nw; ++w) t += red[w]; s_mean = t / (double)len; }
+    __syncthreads();
+    const double m = s_mean;
+    double q = 0.0;
+    for (int i = threadIdx.x; i < len; i += blockDim.x) { const double d = (double)xr[i] - m; q += d * d; }
+    q = mn_warp_sum_d(q);
+    __syncthreads();
+    if (lane == 0) red[warp] = q;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < nw; ++w) t += red[w];
+        mean[blockIdx.x] = (float)m;
+        stdv[blockIdx.x] = sqrtf((float)(t / (double)(len > 1 ? len - 1 : 1)) + eps);
+    }
+}
+
+__global__ void adain_rows_kernel(const float* __restrict__ prior, const float* __restrict__ pm, const float* __restrict__ ps,
+                                  const float* __restrict__ lm, const float* __restrict__ ls, float* __restrict__ out, int len) {
+    mn_pdl_prologue();
+    const size_t base = (size_t)blockIdx.x * len;
+    const float m = pm[blockIdx.x], sd = ps[blockIdx.x], a = ls[blockIdx.x], b = lm[blockIdx.x];
+    for (int i = threadIdx.x; i < len; i += blockDim.x) out[base + i] = (prior[base + i] - m) / sd * a + b;
+}
+
 }  // namespace
+
+extern "C" int mn_swish(const float* x, float* y, long long n, void* stream) {
+    MN_REQUIRE(x && y && n >= 0, "mn_swish: bad args");
+    if (n == 0) return MN_OK;
+    const int blocks = (int)(mn_cdiv64(n, 256) < 148 * 8 ? mn_cdiv64(n, 256) : 148 * 8);
+    MN_CUDA_CHECK(mn_launch(swish_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, x, y, (int64_t)n));
+    return MN_OK;
+}
+
+extern "C" int mn_row_mean_std(const float* x, float* mean, float* stdv, int rows, int len, float eps, void* stream) {
+    MN_REQUIRE(x && mean && stdv && rows > 0 && len > 0, "mn_row_mean_std: bad args");
+    MN_CUDA_CHECK(mn_launch(row_mean_std_kernel, dim3(rows), dim3(256), 0, (cudaStream_t)stream, x, mean, stdv, len, eps));
+    return MN_OK;
+}
+
+extern "C" int mn_adain_rows(const float* prior, const float* prior_mean, const float* prior_std, const float* lq_mean,
+                             const float* lq_std, float* out, int rows, int len, void* stream) {
+    MN_REQUIRE(prior && prior_mean && prior_std && lq_mean && lq_std && out && rows > 0 && len > 0, "mn_adain_rows: bad args");
+    MN_CUDA_CHECK(mn_launch(adain_rows_kernel, dim3(rows), dim3(256), 0, (cudaStream_t)stream, prior, prior_mean, prior_std, lq_mean, lq_std, out, len));
+    return MN_OK;
+}
 
 static int gn_check(const float* x, int x_cs, int N, int H, int W, int C, int cpg) {
     MN_REQUIRE(x && N > 0 && H > 0 && W > 0 && C > 0, "groupnorm: bad dims");

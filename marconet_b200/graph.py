@@ -110,3 +110,4 @@ class GraphedLines:
     def check(self):
         """Synchronising read of the deferred error bits of the last replay; raises like the eager modules."""
         ops.raise_deferred(int(self.flag.item()))
+        ops.check_range(self.device)        # fp16-range guard: the captured precision plan is baked in -- build a new GraphedLines after it fires

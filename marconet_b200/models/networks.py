@@ -54,6 +54,7 @@ class _PackedModule(nn.Module):
         if first.device != device:
             raise RuntimeError(f"marconet_b200: module parameters live on {first.device} but the input is on {device}; "
                                f"call .to(device) first (test_sr.py:66-68 does)")
+        ops.poll_range(device)      # a previous call that overflowed the fp16 split re-routes its layer before we launch again
         key = (device, tuple(p._version for p in self.parameters()))
         if self._packed is None or self._packed_key != key:
             with torch.no_grad():
@@ -68,10 +69,10 @@ class _PackedModule(nn.Module):
                                f"CUDA (sm_100a) devices and has no CPU fallback")
 
 
-def _pack_conv_weight(w):
+def _pack_conv_weight(w, name=None):
     """[Cout, Cin, KH, KW] -> ops.ConvWeight (K-major [KH*KW*Cin, Cout] fp32 + lazily split 16-bit planes)."""
     cout, cin, kh, kw = w.shape
-    return ops.ConvWeight(w.permute(2, 3, 1, 0).reshape(kh * kw * cin, cout).contiguous(), kh * kw)
+    return ops.ConvWeight(w.permute(2, 3, 1, 0).reshape(kh * kw * cin, cout).contiguous(), kh * kw, name=name)
 
 
 # =========================================================================================
@@ -86,16 +87,17 @@ class TextContextEncoderV2(_PackedModule):
         self.transformer = TextViT(num_classes=num_classes, dim=512, max_length=16)
 
     def _pack(self, device):
-        return dict(resnet=self.resnet.pack(), vit=self.transformer.pack())
+        return dict(resnet=self.resnet.pack("encoder.resnet"), vit=self.transformer.pack("encoder.transformer"))
 
     @torch.no_grad()
     def forward(self, lq, _branch=None):
         """``_branch`` (stream, scratch): see TextViT.run -- logits / locs are produced on that stream and the caller joins it."""
         self._need_cuda(lq, "TextContextEncoderV2")
-        pk = self._get_packed(lq.device)
-        x = ops.nchw_to_nhwc(lq.float())
-        feat = self.resnet.run(pk["resnet"], x)
-        return self.transformer.run(pk["vit"], feat, branch=_branch)
+        with ops.on_device(lq):
+            pk = self._get_packed(lq.device)
+            x = ops.nchw_to_nhwc(lq.float())
+            feat = self.resnet.run(pk["resnet"], x)
+            return self.transformer.run(pk["vit"], feat, branch=_branch)
 
 
 # =========================================================================================
@@ -224,7 +226,7 @@ class TextGenerator(_PackedModule):
         for i, m in enumerate(styled):
             w = m.conv.weight[0] * m.conv.scale                      # [Cout, Cin, 3, 3]  (networks.py:284)
             pk["styled"].append(dict(
-                w=_pack_conv_weight(w), wsq=w.pow(2).sum([2, 3]).t().contiguous(),   # [Cin, Cout]
+                w=_pack_conv_weight(w, "tspgan." + ("conv1" if i == 0 else f"convs.{i - 1}")), wsq=w.pow(2).sum([2, 3]).t().contiguous(),   # [Cin, Cout]
                 bias=(m.bias.reshape(-1) + m.activate.bias).contiguous(),
                 off=offs[i], up=m.conv.upsample, cout=w.shape[0]))
         pk["rgb"] = []
@@ -247,6 +249,10 @@ class TextGenerator(_PackedModule):
         """``_branch``: a second CUDA stream for the ToRGB chain (the 128-px prior image), which the feature taps -- and hence the
         SR decoder -- do not depend on; the CALLER joins that stream before it reads the image."""
         self._need_cuda(styles, "TSPGAN")
+        with ops.on_device(styles):
+            return self._forward(styles, labels, _branch)
+
+    def _forward(self, styles, labels, _branch):
         dev = styles.device
         pk = self._get_packed(dev)
         if labels.dim() != 2:
@@ -292,6 +298,7 @@ class TextGenerator(_PackedModule):
                 return ops.torgb(y, s_of(r), r["w"], r["bias"], skip)
             _branch.wait_stream(main)                               # y (and s_all) are ready on the main stream
             y.record_stream(_branch)
+            s_all.record_stream(_branch)                            # the style slices are read on the branch after forward() returns
             with torch.cuda.stream(_branch):
                 out = ops.torgb(y, s_of(r), r["w"], r["bias"], skip)
             out.record_stream(main)
@@ -307,7 +314,10 @@ class TextGenerator(_PackedModule):
             xm = styled(ia, xu, False, next_i=ib)                    # only the pre-modulated operand of conv b is kept
             y = styled(ib, xm, True)
             skip = rgb(y, pk["rgb"][1 + j], skip)
-            taps[y.shape[1]] = y
+            taps[y.shape[2]] = y                                     # the reference picks its taps by WIDTH (networks.py:153-158)
+        if 64 not in taps or 32 not in taps:
+            raise RuntimeError(f"labels [N, {l}]: no feature map is 64 / 32 columns wide (the reference leaves its taps unset, "
+                               f"networks.py:153-158)")
         return ops.as_nchw_view(skip), ops.as_nchw_view(taps[64]), ops.as_nchw_view(taps[32])
 
 
@@ -343,10 +353,10 @@ class _SNConv(nn.Module):
         self.register_buffer("weight_u", u)
         self.register_buffer("weight_v", v)
 
-    def packed(self):
+    def packed(self, name=None):
         w = self.weight_orig
         sigma = torch.dot(self.weight_u, torch.mv(w.flatten(1), self.weight_v))
-        return _pack_conv_weight(w / sigma), self.bias.contiguous()
+        return _pack_conv_weight(w / sigma, name), self.bias.contiguous()
 
 
 class _Slot(nn.Module):
@@ -378,11 +388,12 @@ class ResTextBlockV2(nn.Module):
         if self.in_channels != self.out_channels:
             self.conv_out = nn.Conv2d(in_channels, self.out_channels, kernel_size=1, stride=1, padding=0)
 
-    def packed(self):
-        d = dict(n1=(self.norm1.weight.contiguous(), self.norm1.bias.contiguous()), c1=self.conv1.packed(),
-                 n2=(self.norm2.weight.contiguous(), self.norm2.bias.contiguous()), c2=self.conv2.packed(), co=None)
+    def packed(self, name=None):
+        nm = (lambda s: None) if name is None else (lambda s: f"{name}.{s}")
+        d = dict(n1=(self.norm1.weight.contiguous(), self.norm1.bias.contiguous()), c1=self.conv1.packed(nm("conv1")),
+                 n2=(self.norm2.weight.contiguous(), self.norm2.bias.contiguous()), c2=self.conv2.packed(nm("conv2")), co=None)
         if self.in_channels != self.out_channels:
-            d["co"] = (_pack_conv_weight(self.conv_out.weight), self.conv_out.bias.contiguous())
+            d["co"] = (_pack_conv_weight(self.conv_out.weight, nm("conv_out")), self.conv_out.bias.contiguous())
         return d
 
 
@@ -460,18 +471,18 @@ class TSPSRNet(_PackedModule):
         for name in ("conv_first_8", "conv_body_16", "conv_body_32", "conv_32_scale", "conv_32_shift", "conv_32_to256",
                      "conv_64_scale", "conv_64_shift"):
             seq = getattr(self, name)
-            pk[name] = (seq[0].packed(), seq[2].packed())
-        pk["first_32"] = self.conv_first_32[0].packed()
-        pk["first_16"] = self.conv_first_16[0].packed()
-        pk["up_1"] = self.conv_up[1].packed()
-        pk["up_res"] = self.conv_up[3].packed()
-        pk["up_4"] = self.conv_up[4].packed()
-        pk["fin_0"] = self.conv_final[0].packed()
-        pk["fin_3"] = self.conv_final[3].packed()
-        pk["fin_res"] = self.conv_final[5].packed()
-        pk["fin_6"] = self.conv_final[6].packed()
-        pk["fuse32"] = self.conv_32_fuse[0].packed()
-        pk["fuse64"] = self.conv_64_fuse[0].packed()
+            pk[name] = (seq[0].packed(f"sr.{name}.0"), seq[2].packed(f"sr.{name}.2"))
+        pk["first_32"] = self.conv_first_32[0].packed("sr.conv_first_32.0")
+        pk["first_16"] = self.conv_first_16[0].packed("sr.conv_first_16.0")
+        pk["up_1"] = self.conv_up[1].packed("sr.conv_up.1")
+        pk["up_res"] = self.conv_up[3].packed("sr.conv_up.3")
+        pk["up_4"] = self.conv_up[4].packed("sr.conv_up.4")
+        pk["fin_0"] = self.conv_final[0].packed("sr.conv_final.0")
+        pk["fin_3"] = self.conv_final[3].packed("sr.conv_final.3")
+        pk["fin_res"] = self.conv_final[5].packed("sr.conv_final.5")
+        pk["fin_6"] = self.conv_final[6].packed("sr.conv_final.6")
+        pk["fuse32"] = self.conv_32_fuse[0].packed("sr.conv_32_fuse.0")
+        pk["fuse64"] = self.conv_64_fuse[0].packed("sr.conv_64_fuse.0")
         return pk
 
     def _line_first(self, counts, dev):
@@ -555,11 +566,16 @@ class TSPSRNet(_PackedModule):
         """Public handle on the LR trunk so that a pipeline can launch it early, on a second stream, while the encoder and the
         prior generator run (it needs only the LR line): pass the result to forward(..., _trunk=...)."""
         self._need_cuda(lq, "TSPSRNet")
-        return self._trunk(self._get_packed(lq.device), lq)
+        with ops.on_device(lq):
+            return self._trunk(self._get_packed(lq.device), lq)
 
     @torch.no_grad()
     def forward(self, lq, priors64, priors32, locs, _trunk=None):
         self._need_cuda(lq, "TSPSRNet")
+        with ops.on_device(lq):
+            return self._forward(lq, priors64, priors32, locs, _trunk)
+
+    def _forward(self, lq, priors64, priors32, locs, _trunk):
         dev = lq.device
         pk = self._get_packed(dev)
         d = self.dim
@@ -597,4 +613,18 @@ class TSPSRNet(_PackedModule):
 
 
 def swish(x):
-    raise RuntimeError("swish is fused into mn_groupnorm_swish in marconet_b200 (no standalone CPU op)")
+    """reference networks.py:492-493 (the hot path fuses it into the GroupNorm apply; this is the standalone function)."""
+    with ops.on_device(x):
+        return ops.swish(x.float())
+
+
+def calc_mean_std_4D(feat, eps=1e-5):
+    """reference networks.py:518-525."""
+    with ops.on_device(feat):
+        return ops.calc_mean_std_4d(feat.float(), eps)
+
+
+def adaptive_instance_normalization(prior_feat, lq_feat):
+    """reference networks.py:528-533 (the hot path uses the fused, window-aware mn_adain_concat)."""
+    with ops.on_device(prior_feat):
+        return ops.adaptive_instance_normalization(prior_feat.float(), lq_feat.float())

@@ -15,9 +15,9 @@ from ..ops import ACT_RELU
 _STAGES = ((32, 3, (2, 1)), (64, 4, (1, 1)), (128, 6, (2, 1)), (256, 6, (1, 1)), (512, 3, (1, 1)))
 
 
-def _pack(w):
+def _pack(w, name=None):
     cout, cin, kh, kw = w.shape
-    return ops.ConvWeight(w.detach().permute(2, 3, 1, 0).reshape(kh * kw * cin, cout).contiguous(), kh * kw)
+    return ops.ConvWeight(w.detach().permute(2, 3, 1, 0).reshape(kh * kw * cin, cout).contiguous(), kh * kw, name=name)
 
 
 def conv1x1(in_planes, out_planes, stride=1):
@@ -38,9 +38,10 @@ class BasicBlock(nn.Module):
         self.downsample = downsample
         self.stride = stride if isinstance(stride, tuple) else (stride, stride)
 
-    def pack(self):
-        return dict(c1=_pack(self.conv1.weight), c2=_pack(self.conv2.weight), stride=self.stride,
-                    ds=None if self.downsample is None else _pack(self.downsample[0].weight))
+    def pack(self, name=None):
+        nm = (lambda s: None) if name is None else (lambda s: f"{name}.{s}")
+        return dict(c1=_pack(self.conv1.weight, nm("conv1")), c2=_pack(self.conv2.weight, nm("conv2")), stride=self.stride,
+                    ds=None if self.downsample is None else _pack(self.downsample[0].weight, nm("downsample.0")))
 
 
 class ResNet(nn.Module):
@@ -63,11 +64,11 @@ class ResNet(nn.Module):
                 n = m.kernel_size[0] * m.kernel_size[1] * m.out_channels
                 m.weight.data.normal_(0, math.sqrt(2.0 / n))
 
-    def pack(self):
+    def pack(self, name="resnet"):
         blocks = []
         for li in range(1, 6):
-            blocks += [b.pack() for b in getattr(self, f"layer{li}")]
-        return dict(stem=_pack(self.conv1.weight), blocks=blocks)
+            blocks += [b.pack(f"{name}.layer{li}.{bi}") for bi, b in enumerate(getattr(self, f"layer{li}"))]
+        return dict(stem=_pack(self.conv1.weight, f"{name}.conv1"), blocks=blocks)
 
     @staticmethod
     def run(pk, x):

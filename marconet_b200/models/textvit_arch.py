@@ -15,9 +15,9 @@ from .. import ops
 from ..ops import ACT_GELU, ACT_SIGMOID
 
 
-def _lin(m):
+def _lin(m, name=None):
     """nn.Linear -> ([in,out] packed weight, bias or None)."""
-    return ops.ConvWeight(m.weight.detach().t().contiguous(), 1), (None if m.bias is None else m.bias.detach().contiguous())
+    return ops.ConvWeight(m.weight.detach().t().contiguous(), 1, name=name), (None if m.bias is None else m.bias.detach().contiguous())
 
 
 def _ln(m):
@@ -92,7 +92,7 @@ class TextViT(nn.Module):
         self.linear_w = nn.Sequential(nn.LayerNorm(dim), nn.Linear(dim, 512))
         self.linear_w_maxlen = nn.Sequential(nn.LayerNorm(64), nn.Linear(64, 1))
 
-    def pack(self):
+    def pack(self, name="transformer"):
         t = self.transformer
         dev = self.linear_cls[1].weight.device
         return dict(

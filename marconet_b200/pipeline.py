@@ -43,11 +43,21 @@ def load_checkpoint(model, path_or_dict, prefer_ema=True, strict=True):
 
 
 @torch.no_grad()
-def restore_lines(encoder, tspgan, sr, lq, labels=None, locs=None, max_chars=16):
+def restore_lines(encoder, tspgan, sr, lq, labels=None, locs=None, max_chars=16, check_range=True):
     """LQ lines [B,3,32,512] -> dict(sr, prior, labels, locs, w, logits).
 
     labels: optional list (per line) of int64 [n_b, 1] tensors; default = the encoder's decoded labels (at most ``max_chars``).
-    locs:   optional [B, 2*n] (centre, half-width) in units of the line width; default = converted encoder boxes."""
+    locs:   optional [B, 2*n] (centre, half-width) in units of the line width; default = converted encoder boxes.
+    check_range: synchronise at the end and look at the fp16-range flags (ops.poll_range); when a tensor-core conv overflowed the
+    fp16 hi/lo split its layer is re-routed to the bf16 split and the step is re-run (at most 3 times) -- the caller never sees
+    the Inf/NaN result."""
+    if check_range:
+        from . import ops
+        for attempt in range(4):
+            out = restore_lines(encoder, tspgan, sr, lq, labels, locs, max_chars, check_range=False)
+            torch.cuda.synchronize(lq.device)
+            if not ops.poll_range(lq.device) or attempt == 3:
+                return out
     logits, locs_lr, w = encoder(lq)
     if labels is None:
         labels = []
@@ -109,3 +119,108 @@ def restore_image(encoder, tspgan, sr, img_u8, labels, boxes):
     show_w = ops.round_half_even(img.shape[1] * (128 / h))    # ShowLQ = cv2.resize(img, fx=128/h, ...) (test_sr.py:98)
     sr_u8 = ops.postprocess_sr(out)[0, :, :show_w]            # ShowSR = sr[:, :ShowLQ.shape[1]] (test_sr.py:201)
     return dict(sr_u8=sr_u8, sr=out, lq=lq, lq_width=lq_w, prior=img_prior, locs=locs)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Per-layer precision plan: fp16x3 / bf16x3 / fp32 and a power-of-two input scale per conv layer,
+# chosen on calibration inputs against the exact fp32 kernels.  Needed the day real checkpoints replace the synthetic ones: the
+# default fp16 hi/lo split (conv_tc2.cu) has fp32-grade mantissa but fp16's exponent range.
+# ---------------------------------------------------------------------------------------------------------------------
+def conv_layers(*modules):
+    """Every ops.ConvWeight of the (already used, hence packed) modules, in pack order."""
+    from . import ops
+    out, seen = [], set()
+
+    def walk(o):
+        if isinstance(o, ops.ConvWeight):
+            if id(o) not in seen:
+                seen.add(id(o)); out.append(o)
+        elif isinstance(o, dict):
+            for v in o.values():
+                walk(v)
+        elif isinstance(o, (list, tuple)):
+            for v in o:
+                walk(v)
+
+    for m in modules:
+        for sub in m.modules():
+            walk(getattr(sub, "_packed", None))
+    return out
+
+
+@torch.no_grad()
+def tune_precision(encoder, tspgan, sr, lq, labels=None, locs=None, target_absmax=1024.0, fp32_fallback=1e-3, compare=True):
+    """Calibrate the per-layer precision plan on (lq, labels, locs) -- representative LR lines -- and install it (ops.PLAN).
+
+    pass 1 (range-safe bf16 split everywhere): max |input| of every tensor-core conv -> x_scale = 2^k with
+            |x| * x_scale ~ ``target_absmax`` (64x headroom below 65504, inputs down to 2^-24 * target keep full hi/lo precision);
+    pass 2 (``compare``): every such layer also runs through the exact fp32 kernel and through both split formats; the format with
+            the smaller relative max-abs error wins, and a layer whose best error still exceeds ``fp32_fallback`` (relative to its
+            output's max) runs on the fp32 CUDA-core kernel;
+    pass 3: the plan is verified -- one more step, no range flag may rise.
+    Returns a list of dict(name, absmax, x_scale, precision, err_f16x3, err_bf16x3), one per tensor-core conv layer."""
+    import math
+    from . import ops
+    dev = lq.device
+    with torch.cuda.device(dev):
+        old_default = ops.default_precision()
+        restore_lines(encoder, tspgan, sr, lq, labels, locs, check_range=False)     # packs the weights
+        layers = conv_layers(encoder, tspgan, sr)
+        for cw in layers:
+            cw.set_plan(x_scale=1.0)
+            cw.precision = None
+            ops.PLAN[cw.name] = (None, 1.0)
+        try:
+            ops.set_default_precision(ops.PREC_BF16X3_TC)
+            with ops.calibration(dev) as cal:
+                restore_lines(encoder, tspgan, sr, lq, labels, locs, check_range=False)
+            res = cal.results()
+        finally:
+            ops.set_default_precision(old_default)
+        ops.poll_range(dev, reroute=False)
+        for cw, r in res.items():
+            a = r["absmax"]
+            k = 0 if not (a > 0 and math.isfinite(a)) else max(-24, min(24, round(math.log2(target_absmax / a))))
+            cw.set_plan(x_scale=2.0 ** k)
+        errs = {}
+        if compare:
+            with ops.calibration(dev, compare=True) as cal:
+                restore_lines(encoder, tspgan, sr, lq, labels, locs, check_range=False)
+            errs = cal.results()
+            ops.poll_range(dev, reroute=False)
+        report = []
+        for cw, r in res.items():
+            e = errs.get(cw, {})
+            e16, ebf = e.get("err_f16x3", float("nan")), e.get("err_bf16x3", float("nan"))
+            prec = ops.PREC_F16X3_TC
+            if compare and cw in errs:
+                prec = ops.PREC_F16X3_TC if (e16 <= ebf or not math.isfinite(ebf)) and math.isfinite(e16) else ops.PREC_BF16X3_TC
+                if not (min(e16, ebf) <= fp32_fallback):
+                    prec = ops.PREC_FP32_SIMT
+            cw.set_plan(precision=prec)
+            report.append(dict(name=cw.name, absmax=r["absmax"], x_scale=cw.x_scale, precision=prec, err_f16x3=e16, err_bf16x3=ebf))
+        restore_lines(encoder, tspgan, sr, lq, labels, locs, check_range=False)
+        torch.cuda.synchronize(dev)
+        ops.check_range(dev)
+    return report
+
+
+def save_precision_plan(path):
+    """ops.PLAN -> JSON {layer name: [precision or null, x_scale]}."""
+    import json
+    from . import ops
+    with open(path, "w") as f:
+        json.dump({k: [v[0], v[1]] for k, v in ops.PLAN.items()}, f, indent=1, sort_keys=True)
+
+
+def load_precision_plan(path_or_dict, *modules):
+    """Install a saved plan; already-packed layers of ``modules`` are updated in place, later packs pick it up by name."""
+    import json
+    from . import ops
+    plan = json.load(open(path_or_dict)) if isinstance(path_or_dict, str) else path_or_dict
+    for k, (prec, xs) in plan.items():
+        ops.PLAN[k] = (None if prec is None else int(prec), float(xs))
+    for cw in conv_layers(*modules):
+        if cw.name in ops.PLAN:
+            cw.precision, cw.x_scale = ops.PLAN[cw.name]
+    return plan

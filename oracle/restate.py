@@ -216,8 +216,8 @@ def tspgan_forward(sd, styles, labels, dtype=torch.float32, return_all=False):
         out = _styled_conv(sd, f"{g}convs.{2 * j}.", out, latent, True)
         out = _styled_conv(sd, f"{g}convs.{2 * j + 1}.", out, latent, False)
         skip = _to_rgb(sd, f"{g}to_rgbs.{j}.", out, latent, skip)
-        taps[out.shape[-2]] = out
-        taps[("rgb", out.shape[-2])] = skip
+        taps[out.shape[-1]] = out                      # the reference keys its taps on the WIDTH (networks.py:153-158)
+        taps[("rgb", out.shape[-1])] = skip
     if return_all:
         return skip, taps[64], taps[32], taps
     return skip, taps[64], taps[32]

@@ -173,3 +173,53 @@ def test_char_windows_match_a_literal_restatement_on_random_boxes():
                 for x in range(x1, x2):
                     expect[x] = b * 64 + c
             assert owner[b] == expect
+
+
+def test_launch_context_is_per_thread():
+    """ops.use_workspace / ops.deferred_checks are thread-local: a second host thread must not see the scratch or the
+    error flag another thread installed."""
+    import threading
+    from marconet_b200 import ops
+
+    class _Fake:            # stands in for a CUDA tensor: deferred_checks only validates real flags when they are not None
+        pass
+
+    seen = {}
+    ready, done = threading.Event(), threading.Event()
+
+    def other():
+        ready.wait(5)
+        seen["ws"] = getattr(ops._TLS, "ws_override", None)
+        seen["flag"] = ops.deferred_flag()
+        done.set()
+
+    t = threading.Thread(target=other)
+    t.start()
+    marker = _Fake()
+    with ops.use_workspace(marker):
+        ops._TLS.deferred_flag = marker
+        try:
+            assert ops.workspace(None) is marker and ops.deferred_flag() is marker
+            ready.set()
+            done.wait(5)
+        finally:
+            ops._TLS.deferred_flag = None
+    t.join()
+    assert seen == {"ws": None, "flag": None}
+
+
+def test_precision_plan_survives_repack_by_name():
+    """ops.PLAN is keyed by layer name: a ConvWeight re-created under the same name picks its precision / input scale up again."""
+    import torch
+    from marconet_b200 import ops
+    saved = dict(ops.PLAN)
+    try:
+        a = ops.ConvWeight(torch.zeros(9 * 64, 64), 9, name="test.plan_layer")
+        assert (a.precision, a.x_scale) == (None, 1.0)
+        a.set_plan(precision=ops.PREC_BF16X3_TC, x_scale=0.25)
+        b = ops.ConvWeight(torch.zeros(9 * 64, 64), 9, name="test.plan_layer")
+        assert (b.precision, b.x_scale) == (ops.PREC_BF16X3_TC, 0.25)
+        assert ops.ConvWeight.from_tag(b.tag) is b
+    finally:
+        ops.PLAN.clear()
+        ops.PLAN.update(saved)
