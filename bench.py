@@ -155,30 +155,51 @@ def cpu_line_seconds(chars, repeats=1, threads=None):
     return best, threads
 
 
+def workload_string(lines, chars):
+    """One wording for both arms (the driver compares the `config.workload` strings of the two JSON lines)."""
+    return (f"{lines} synthetic 32x512 LR line(s) x {chars} chars per GPU per step, "
+            f"encoder->TSPGAN->TSPSRNet (BASELINE configs[1])")
+
+
+PIN = ("oracle/restate.py = the reference's torch CPU path restated op for op; pinned bit-identical (max |diff| = 0.0) to the "
+       "unmodified reference modules by tests/test_oracle.py::test_oracle_is_bit_identical_to_reference_modules and against "
+       "tests/golden/*.npz generated from them (oracle/make_golden.py, oracle/make_golden2.py)")
+
+
 def run_reference_arm(args):
+    """The reference's own CPU implementation of the path on the box's host cores, one rank only.  The reference is Python and
+    cannot travel to the GPU box (no /root/reference there), so the arm runs its pinned restatement (kind "port")."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
-    chars = args.chars
+    chars, lines = args.chars, args.lines
     budget_s = 150.0
-    t_first, threads = cpu_line_seconds(chars, 1)                      # warm-up step (also sizes the run)
-    steps = max(1, min(args.steps, int(budget_s // max(t_first, 1e-3))))
+    warm = max(1, args.warmup)
+    t_first, threads = cpu_line_seconds(chars, 1)                      # first warm-up step (also sizes the run)
+    per_step = max(t_first, 1e-3) * lines
+    warm = max(1, min(warm, int(30.0 // per_step)))                    # honour --warmup within a bounded CPU budget
+    for _ in range(warm - 1):
+        for _ in range(lines):
+            cpu_line_seconds(chars, 1)
+    steps = max(1, min(args.steps, int(budget_s // per_step)))
     times = []
     for _ in range(steps):
-        t, _ = cpu_line_seconds(chars, 1)
+        t = 0.0
+        for _ in range(lines):                                         # the reference restores one line at a time (test_sr.py:77)
+            t += cpu_line_seconds(chars, 1)[0]
         times.append(t)
     ms = 1e3 * sum(times) / len(times)
-    value = chars / (ms / 1e3)
+    value = lines * chars / (ms / 1e3)
     rec = {
         "impl": "reference", "metric": "sr_chars_per_sec", "value": value, "unit": "chars/s", "n_gpus": args.gpus, "steps": steps,
-        "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": f"1 synthetic 32x512 LR line x {chars} chars, encoder->TSPGAN->TSPSRNet (BASELINE configs[1])",
-                   "lines_per_step": 1, "chars_per_line": chars},
+        "config": {"workload": workload_string(lines, chars), "lines_per_step_per_gpu": lines, "chars_per_line": chars,
+                   "note": "one CPU process on rank 0 whatever --gpus says: per-N ratios against this arm are only meaningful at N=1"},
         "cpu_baseline": {"value": value, "unit": "chars/s", "cores": threads, "kind": "port",
-                         "sample": f"{steps} x one full {chars}-char line through oracle/restate.py (bit-identical restatement of the "
-                                   f"reference's torch CPU path), torch {torch.__version__}, {threads} threads"},
+                         "sample": f"{steps} step(s) of {lines} full {chars}-char line(s), torch {torch.__version__} CPU fp32, {threads} threads "
+                                   f"(its fastest setting of those probed). " + PIN},
         "e2e": {"value": value, "unit": "chars/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -304,6 +325,9 @@ def run_ours(args):
         ms_e2e = timed(e2e_step, args.steps)
 
         roof = modconv_roofline(nets["tspgan"], chars, dev) if rank == 0 else None
+        collective = None
+        if not args.no_collective:
+            collective = collective_record(nets, world, rank, dev, args)
 
         # informational: end to end through GraphedLines (this repo's own extension API) with the same host buffers and copies.
         # Single process only (no collectives inside, so a failure here cannot desynchronise ranks); runs last.
@@ -344,13 +368,12 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             t, threads = cpu_line_seconds(chars, 1)
             cpu = {"value": chars / t, "unit": "chars/s", "cores": threads, "kind": "port",
-                   "sample": f"one full {chars}-char 32x512 line through oracle/restate.py (torch CPU fp32, {threads} threads)"}
+                   "sample": f"one full {chars}-char 32x512 line, torch CPU fp32, {threads} threads. " + PIN}
         rec = {
             "metric": "sr_chars_per_sec", "value": value, "unit": "chars/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{lines} synthetic 32x512 LR line(s) x {chars} chars per GPU per step, "
-                                   f"encoder->TSPGAN->TSPSRNet (BASELINE configs[1])",
+            "config": {"workload": workload_string(lines, chars),
                        "lines_per_step_per_gpu": lines, "chars_per_line": chars, "parallelism": f"line-sharded dp{world}, no collective",
                        "precision": {0: "fp32 CUDA-core", 1: "fp16x3 tcgen05", 2: "bf16x3 tcgen05", 3: "fp16 tcgen05"}[ops.default_precision()],
                        "l2": "weights (352 MB fp32) + activations (>1 GB/line) exceed the 126 MB L2; no flush needed",
@@ -365,10 +388,150 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": roof,
             "cpu_baseline": cpu,
+            "collective": collective,
         }
+        rec["config"]["tc_fallback_shapes"] = len(ops.TC_FALLBACKS)
         print(json.dumps(rec), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def collective_record(nets, world, rank, dev, args):
+    """The north_star's REAL multi-GPU split, driver-visible: characters sharded over ranks with an
+    exchange of the prior features the SR decoder consumes (reference consumer: networks.py:442-445, 475-478).
+
+    priors1024  BASELINE configs[2]: 1024 (label, w) pairs, prior generation only, STRONG scaling (1024 characters in total
+                whatever N is): block-cyclic character shards, compute only vs + owner-only all-to-all (each line's priors go to
+                the rank that owns the line) vs + the round-1 all-gather to every rank.
+    lines64     BASELINE configs[3]: 64 lines x 16 characters end to end (64/N lines per rank): line-sharded (no exchange) vs
+                character-sharded priors (encoder on owned lines -> all-gather of w (2 KB/line) -> block-cyclic TSPGAN ->
+                all-to-all of fea64/fea32 to the line owners -> TSPSRNet on owned lines).
+    Every number: CUDA events, barrier + synchronize on both sides, max over ranks.  Collectives are NCCL over NVLink."""
+    import torch
+    import torch.distributed as dist
+    from marconet_b200 import parallel
+    from marconet_b200.testing import synth
+    W = world
+    steps = 3
+
+    def timed(fn):
+        for _ in range(2):
+            fn()
+        if W > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+        if W > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.barrier()
+        return float(ms.item())
+
+    out = {}
+    gen, enc, sr = nets["tspgan"], nets["encoder"], nets["sr"]
+    chunk = 128                                     # characters per TSPGAN call (bounds activation memory at N=1)
+    with torch.no_grad():
+        # ---------------- configs[2]: 1024 random (label, w) pairs, prior only
+        n = 1024
+        if n % (W * W) == 0:
+            labels = synth.make_labels(n, 11).to(dev)
+            styles = synth.make_styles(n, 11).to(dev)
+            own = n // W
+
+            def run_priors(mode):
+                # generated in `chunk`-character calls per rank; every chunk of W*chunk_local characters is its own block-cyclic round
+                per_call = min(chunk * W, n)
+                for c0 in range(0, n, per_call):
+                    s_, l_ = styles[c0:c0 + per_call], labels[c0:c0 + per_call]
+                    if mode == "all_gather":
+                        parallel.generate_priors_sharded(gen, s_, l_)
+                    else:
+                        parallel.generate_priors_for_owners(gen, s_, l_, exchange=(mode == "all_to_all"))
+
+            ms_c = timed(lambda: run_priors("compute"))
+            rec = {"chars_total": n, "chars_per_rank": own, "scaling": "strong", "ms_compute_only": ms_c,
+                   "chars_per_sec_compute_only": n / (ms_c / 1e3)}
+            if W > 1:
+                ms_a2a = timed(lambda: run_priors("all_to_all"))
+                ms_ag = timed(lambda: run_priors("all_gather"))
+                b = parallel.exchange_bytes_per_rank(n, W)
+                rec.update({"ms_with_all_to_all": ms_a2a, "chars_per_sec_with_all_to_all": n / (ms_a2a / 1e3),
+                            "all_to_all_bytes_sent_per_rank": b["all_to_all"],
+                            "all_to_all_gbps_per_rank": b["all_to_all"] / max(ms_a2a - ms_c, 1e-3) / 1e6,
+                            "ms_with_all_gather": ms_ag, "chars_per_sec_with_all_gather": n / (ms_ag / 1e3),
+                            "all_gather_bytes_received_per_rank": b["all_gather"],
+                            "all_gather_gbps_per_rank": b["all_gather"] / max(ms_ag - ms_c, 1e-3) / 1e6,
+                            "exchange": "NCCL all_to_all_single of fea64+fea32 (6 MiB/char) to line owners; all_gather = round-1 variant"})
+            out["priors1024"] = rec
+            del labels, styles
+        # ---------------- configs[3]: 64 lines x 16 chars end to end
+        L, C = 64, 16
+        if L % W == 0 and (L * C) % (W * W) == 0:
+            lpr = L // W
+            lq_all = synth.make_lq(L, 500)
+            lq_own = lq_all[rank * lpr:(rank + 1) * lpr].to(dev)
+            lab_all = torch.cat([synth.make_labels(C, 500 + b) for b in range(L)], 0).to(dev)
+            lab_own = lab_all[rank * lpr * C:(rank + 1) * lpr * C]
+            locs_own = synth.make_locs(lpr, C).to(dev)
+            lines_per_call = max(1, chunk // C)
+
+            def line_sharded():
+                _, _, w = enc(lq_own)
+                res = []
+                for b0 in range(0, lpr, lines_per_call):             # `chunk` characters (= lines_per_call lines) per TSPGAN / TSPSRNet call
+                    b1 = min(lpr, b0 + lines_per_call)
+                    _, f64, f32_ = gen(styles=w[b0:b1].repeat_interleave(C, dim=0), labels=lab_own[b0 * C:b1 * C], noise=None)
+                    p64 = [f64[i * C:(i + 1) * C] for i in range(b1 - b0)]
+                    p32 = [f32_[i * C:(i + 1) * C] for i in range(b1 - b0)]
+                    res.append(sr(lq_own[b0:b1], p64, p32, locs_own[b0:b1]))
+                return res
+
+            per_call = min(chunk * W, L * C)                # characters per block-cyclic round (all ranks together)
+            rounds = (L * C) // per_call
+            lines_round = per_call // C                     # a round covers this many consecutive global lines ...
+            own_lines = max(1, lines_round // W)            # ... of which this rank owns the rank-th block
+            lq_all_dev = lq_all.to(dev)
+
+            def char_sharded():
+                _, _, w = enc(lq_own)
+                if W > 1:
+                    w_all = torch.empty((L, w.shape[1]), dtype=w.dtype, device=dev)
+                    dist.all_gather_into_tensor(w_all, w.contiguous())      # global line order = rank-major blocks of lq_own
+                else:
+                    w_all = w
+                styles = w_all.repeat_interleave(C, dim=0)
+                res = []
+                for k in range(rounds):
+                    c0 = k * per_call
+                    f64, f32_ = parallel.generate_priors_for_owners(gen, styles[c0:c0 + per_call], lab_all[c0:c0 + per_call])
+                    g0 = k * lines_round + rank * own_lines                 # first global line of this rank's block in round k
+                    p64 = [f64[b * C:(b + 1) * C] for b in range(own_lines)]
+                    p32 = [f32_[b * C:(b + 1) * C] for b in range(own_lines)]
+                    res.append(sr(lq_all_dev[g0:g0 + own_lines], p64, p32, locs_own[:own_lines]))
+                return res
+
+            ms_line = timed(line_sharded)
+            rec = {"lines_total": L, "chars_per_line": C, "lines_per_rank": lpr, "ms_line_sharded_no_exchange": ms_line,
+                   "chars_per_sec_line_sharded": L * C / (ms_line / 1e3)}
+            if W > 1 and lines_ok_for_rounds(L, C, W, chunk):
+                ms_char = timed(char_sharded)
+                b = parallel.exchange_bytes_per_rank(L * C, W)
+                rec.update({"ms_char_sharded_with_all_to_all": ms_char, "chars_per_sec_char_sharded": L * C / (ms_char / 1e3),
+                            "all_to_all_bytes_sent_per_rank": b["all_to_all"], "rounds": rounds,
+                            "exchange": "all_gather of w (2 KB/line) + NCCL all_to_all_single of fea64/fea32 to line owners"})
+            out["lines64"] = rec
+    return out if rank == 0 else None
+
+
+def lines_ok_for_rounds(L, C, W, chunk):
+    """char_sharded() hands every round's owner block to TSPSRNet as whole lines: a round must hold a multiple of W lines."""
+    per_call = min(chunk * W, L * C)
+    return per_call % C == 0 and (per_call // C) % W == 0 and (L * C) % per_call == 0
 
 
 def _time_modconv(e, chars, dev, iters):
@@ -392,6 +555,20 @@ def _time_modconv(e, chars, dev, iters):
     return ms, 2.0 * 512 * 512 * 9 * 32 * 32 * chars
 
 
+def dram_traffic(chars):
+    """roofline.traffic = dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from an `ncu --set
+    full` capture of the CURRENT kernel build summarised in profiles/r2_tc2_dram.json by profiles/summarize_ncu.py (never a
+    literal; null when no capture of this build exists)."""
+    path = os.path.join(ROOT, "profiles", "r2_tc2_dram.json")
+    try:
+        d = json.load(open(path))
+        if int(d.get("chars", -1)) == int(chars):
+            return {"traffic": float(d["dram_bytes_per_launch"]), "traffic_source": "profiles/r2_tc2_dram.json (" + d.get("capture", "ncu --set full") + ")"}
+    except Exception:
+        pass
+    return {"traffic": None}
+
+
 def modconv_roofline(tspgan, chars, dev, iters=20):
     """Live CUDA-event timing of the dominant kernel: the 3x3 modulated conv 512->512 at 32x32 for `chars`
     characters (reference networks.py:294,299 grouped conv; 4.83 GFLOP per character and launch)."""
@@ -407,8 +584,7 @@ def modconv_roofline(tspgan, chars, dev, iters=20):
     passes = {0: 0, 1: 3, 2: 3, 3: 1}[ops.default_precision()]
     return {"kernel": "mn_conv2d_nhwc modulated 3x3 512->512 @32x32 x%d chars (conv_tc2_kernel<128>)" % chars, "bound": "tensor",
             "achieved": achieved, "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_burst"],
-            # dram__bytes_read.sum + dram__bytes_write.sum of this launch from profiles/r1_tc2_ncu_full.txt (ncu --set full)
-            "traffic": 46.6e6 if chars == 16 else None,
+            **dram_traffic(chars),
             "algorithmic_gflop_per_launch": flops / 1e9, "ms_per_launch": ms,
             "mma_passes_per_algorithmic_flop": passes,
             "tensor_pipe_frac": (achieved * passes / peaks["tf_burst"]) if passes else 0.0,
@@ -428,6 +604,7 @@ def main():
     ap.add_argument("--chars", type=int, default=16)
     ap.add_argument("--precision", type=int, default=None, help="0 fp32 CUDA-core, 1 fp16x3 tcgen05 (default), 2 bf16x3, 3 fp16x1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-collective", action="store_true", help="skip the character-sharded configs[2]/[3] sub-records")
     ap.add_argument("--no-graph", action="store_true", help="skip the CUDA-graph replay measurement (value = eager module calls)")
     ap.add_argument("--profile", action="store_true", help="run one step inside cudaProfilerStart/Stop and exit (for ncu)")
     args = ap.parse_args()

@@ -262,6 +262,15 @@ int mn_linear_small_m_ex(const float* x, long long x_row_stride, long long x_bat
                          const float* w, const float* bias, const float* residual, long long res_batch_stride, float* y,
                          int batches, int M, int K, int N, int act, float gain, void* stream);
 
+/* mn_linear_small_m_ex with a caller-owned scratch: deep-K layers (the patch embedding, K = 32768) are additionally split into
+ * outer K slices whose raw partial tiles go to `workspace` (>= slices*batches*M*N floats are used when available) and are added
+ * in slice order by a second kernel that runs the bias / residual / activation epilogue -- deterministic, no atomics.
+ * workspace may be NULL (then identical to mn_linear_small_m_ex). */
+int mn_linear_small_m_ws(const float* x, long long x_row_stride, long long x_batch_stride, int x_seg_len, long long x_seg_stride,
+                         const float* w, const float* bias, const float* residual, long long res_batch_stride, float* y,
+                         int batches, int M, int K, int N, int act, float gain, float* workspace, long long workspace_bytes,
+                         void* stream);
+
 /* LayerNorm over the TOKEN axis followed by Linear(T -> To) over the token axis, i.e. the
  * `x.permute(0,2,1)` -> LayerNorm(T) -> Linear -> permute(0,2,1) idiom at
  * models/textvit_arch.py:154 (T=64 -> 16) and :72 (64 -> 1).  x:[B,T,D] -> out:[B,To,D]. */

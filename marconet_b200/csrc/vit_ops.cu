@@ -49,35 +49,57 @@ __global__ void token_mix_kernel(const float* __restrict__ x, const float* __res
     }
 }
 
-// One CTA per (batch, head).  S <= 64, dh == 64.
-__global__ void __launch_bounds__(256) attention_kernel(const float* __restrict__ qkv, float* __restrict__ out,
-                                                        int S, int heads, float scale) {
+// Fused multi-head attention: one CTA per (batch, head, chunk of QC query rows).  S <= 64, dh == 64.
+// Round 1 ran one CTA per (batch, head) = 8 CTAs on 148 SMs with scalar shared-memory loops (33.5 us per call, 5 calls per
+// line, 3 of them on the step's critical path); splitting the queries gives B*heads*S/QC CTAs, K / V are re-read from L2
+// (32 KB per CTA), and the inner products read shared memory as float4 (K rows padded to 68 floats: conflict-free).
+template <int QC>
+__global__ void __launch_bounds__(128) attention_kernel(const float* __restrict__ qkv, float* __restrict__ out,
+                                                        int S, int heads, int nch, float scale) {
     mn_pdl_prologue();
-    constexpr int DH = 64, SM = 64;
+    constexpr int DH = 64, SM = 64, KP = 68;
     extern __shared__ __align__(16) float att_smem[];
-    float (*Q)[DH] = reinterpret_cast<float (*)[DH]>(att_smem);
-    float (*K)[DH + 1] = reinterpret_cast<float (*)[DH + 1]>(att_smem + SM * DH);
-    float (*V)[DH] = reinterpret_cast<float (*)[DH]>(att_smem + SM * DH + SM * (DH + 1));
-    float (*P)[SM + 1] = reinterpret_cast<float (*)[SM + 1]>(att_smem + 2 * SM * DH + SM * (DH + 1));
-    const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+    float (*Q)[DH] = reinterpret_cast<float (*)[DH]>(att_smem);                       // [QC][64]
+    float (*K)[KP] = reinterpret_cast<float (*)[KP]>(att_smem + QC * DH);              // [64][68]
+    float (*V)[DH] = reinterpret_cast<float (*)[DH]>(att_smem + QC * DH + SM * KP);    // [64][64]
+    float (*P)[KP] = reinterpret_cast<float (*)[KP]>(att_smem + QC * DH + SM * KP + SM * DH);   // [QC][68]
+    const int chunk = blockIdx.x % nch, bh = blockIdx.x / nch;
+    const int b = bh / heads, h = bh % heads;
     const int inner = heads * DH;
-    const float* base = qkv + (size_t)b * S * 3 * inner;
-    for (int idx = threadIdx.x; idx < S * DH; idx += blockDim.x) {
-        const int i = idx / DH, d = idx % DH;
-        const float* r = base + (size_t)i * 3 * inner + h * DH + d;
-        Q[i][d] = r[0]; K[i][d] = r[inner]; V[i][d] = r[2 * inner];
+    const int q0 = chunk * QC;
+    const int nq = min(QC, S - q0);
+    const float* base = qkv + (size_t)b * S * 3 * inner + h * DH;
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < S * (DH / 4); idx += 128) {
+        const int j = idx >> 4, d4 = (idx & 15) * 4;
+        const float* r = base + (size_t)j * 3 * inner + d4;
+        *reinterpret_cast<float4*>(&K[j][d4]) = *reinterpret_cast<const float4*>(r + inner);
+        *reinterpret_cast<float4*>(&V[j][d4]) = *reinterpret_cast<const float4*>(r + 2 * inner);
+    }
+    for (int idx = tid; idx < nq * (DH / 4); idx += 128) {
+        const int i = idx >> 4, d4 = (idx & 15) * 4;
+        *reinterpret_cast<float4*>(&Q[i][d4]) = *reinterpret_cast<const float4*>(base + (size_t)(q0 + i) * 3 * inner + d4);
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < S * S; idx += blockDim.x) {
-        const int i = idx / S, j = idx % S;
-        float acc = 0.f;
-#pragma unroll 16
-        for (int d = 0; d < DH; ++d) acc = fmaf(Q[i][d], K[j][d], acc);
-        P[i][j] = acc * scale;
+    // scores: thread -> key j = tid % 64, query rows i = tid / 64 + 2k
+    {
+        const int j = tid & 63, i0 = tid >> 6;
+        if (j < S) {
+            for (int i = i0; i < nq; i += 2) {
+                float acc = 0.f;
+#pragma unroll
+                for (int d4 = 0; d4 < DH; d4 += 4) {
+                    const float4 q = *reinterpret_cast<const float4*>(&Q[i][d4]);
+                    const float4 k = *reinterpret_cast<const float4*>(&K[j][d4]);
+                    acc = fmaf(q.x, k.x, acc); acc = fmaf(q.y, k.y, acc); acc = fmaf(q.z, k.z, acc); acc = fmaf(q.w, k.w, acc);
+                }
+                P[i][j] = acc * scale;
+            }
+        }
     }
     __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = warp; i < S; i += (blockDim.x >> 5)) {
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int i = warp; i < nq; i += 4) {
         float m = -INFINITY;
         for (int j = lane; j < S; j += 32) m = fmaxf(m, P[i][j]);
         m = mn_warp_max(m);
@@ -88,11 +110,13 @@ __global__ void __launch_bounds__(256) attention_kernel(const float* __restrict_
         for (int j = lane; j < S; j += 32) P[i][j] *= inv;
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < S * DH; idx += blockDim.x) {
-        const int i = idx / DH, d = idx % DH;
-        float acc = 0.f;
-        for (int j = 0; j < S; ++j) acc = fmaf(P[i][j], V[j][d], acc);
-        out[((size_t)b * S + i) * inner + h * DH + d] = acc;
+    {
+        const int d = tid & 63, i0 = tid >> 6;
+        for (int i = i0; i < nq; i += 2) {
+            float acc = 0.f;
+            for (int j = 0; j < S; ++j) acc = fmaf(P[i][j], V[j][d], acc);
+            out[((size_t)b * S + q0 + i) * inner + h * DH + d] = acc;
+        }
     }
 }
 
@@ -127,6 +151,7 @@ struct LinArgs {
     const float* x; long long x_rs, x_bs; int seg_len; long long seg_stride;
     const float* w; const float* bias; const float* residual; long long res_bs;
     float* y; int M, K, N, act; float gain;
+    int ko;            // outer K slices (grid.z = batches * ko): slice q writes its RAW partial tile to y + q*batches*M*N, a second kernel reduces
 };
 
 template <int MT, int NT>
@@ -142,9 +167,11 @@ __global__ void __launch_bounds__(128) linear_small_m_kernel(const LinArgs a) {
     const int n0 = blockIdx.x * NT;
     const int ksplit = gridDim.y;
     const uint32_t krank = ksplit > 1 ? lin_cluster_rank() : 0;
-    const float* xb = a.x + (size_t)blockIdx.z * a.x_bs;
+    const int batch = blockIdx.z / a.ko, kouter = blockIdx.z % a.ko;
+    const float* xb = a.x + (size_t)batch * a.x_bs;
     const int nchunks_all = a.K / 32;
-    const int ch_begin = (int)((long long)nchunks_all * krank / ksplit), ch_end = (int)((long long)nchunks_all * (krank + 1) / ksplit);
+    const int kslices = ksplit * a.ko, kslice = kouter * ksplit + (int)krank;
+    const int ch_begin = (int)((long long)nchunks_all * kslice / kslices), ch_end = (int)((long long)nchunks_all * (kslice + 1) / kslices);
     const int nchunks = ch_end - ch_begin;
     float acc[RPT][CPT];
 #pragma unroll
@@ -218,8 +245,8 @@ __global__ void __launch_bounds__(128) linear_small_m_kernel(const LinArgs a) {
         lin_cluster_sync();                              // peers keep their shared memory alive until rank 0 has read it
         if (krank != 0) return;
     }
-    float* yb = a.y + (size_t)blockIdx.z * a.M * a.N;
-    const float* rb = a.residual ? a.residual + (size_t)blockIdx.z * a.res_bs : nullptr;
+    float* yb = a.y + ((size_t)kouter * (gridDim.z / a.ko) + batch) * a.M * a.N;
+    const float* rb = a.residual ? a.residual + (size_t)batch * a.res_bs : nullptr;
 #pragma unroll
     for (int i = 0; i < RPT; ++i) {
         const int r = rg * RPT + i;
@@ -228,6 +255,7 @@ __global__ void __launch_bounds__(128) linear_small_m_kernel(const LinArgs a) {
         for (int c = 0; c < CPT; ++c) {
             const int o = n0 + cg * CPT + c;
             if (o >= a.N) continue;
+            if (a.ko > 1) { yb[(size_t)r * a.N + o] = acc[i][c]; continue; }       // raw partial: linear_ko_reduce_kernel finishes
             float v = acc[i][c] + (a.bias ? a.bias[o] : 0.f);
             if (rb) v += rb[(size_t)r * a.N + o];
             yb[(size_t)r * a.N + o] = mn_apply_act(v, a.act) * a.gain;
@@ -245,7 +273,7 @@ static cudaError_t launch_linear(const LinArgs& a, int batches, int ksplit, cuda
         if (e != cudaSuccess) return e;
     }
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(mn_cdiv(a.N, NT), ksplit, batches);
+    cfg.gridDim = dim3(mn_cdiv(a.N, NT), ksplit, batches * a.ko);
     cfg.blockDim = dim3(128, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
@@ -263,6 +291,30 @@ static cudaError_t launch_linear(const LinArgs& a, int batches, int ksplit, cuda
     }
     cfg.attrs = attr; cfg.numAttrs = na;
     return cudaLaunchKernelEx(&cfg, linear_small_m_kernel<MT, NT>, a);
+}
+
+// y[b][r][o] = act(sum_q part[q][b][r][o] + bias[o] + residual[b][r][o]) * gain   (q in slice order: deterministic)
+__global__ void linear_ko_reduce_kernel(const float* __restrict__ part, int ko, long long slice_elems, const float* __restrict__ bias,
+                                        const float* __restrict__ residual, long long res_bs, float* __restrict__ y, int M, int N,
+                                        int act, float gain) {
+    mn_pdl_prologue();
+    const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i4 >= slice_elems) return;
+    float4 v = *reinterpret_cast<const float4*>(part + i4);
+    for (int q = 1; q < ko; ++q) {
+        const float4 t = *reinterpret_cast<const float4*>(part + (size_t)q * slice_elems + i4);
+        v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+    }
+    const int o = (int)(i4 % N);
+    const long long row = i4 / N;
+    const int b = (int)(row / M), r = (int)(row % M);
+    if (bias) { v.x += bias[o]; v.y += bias[o + 1]; v.z += bias[o + 2]; v.w += bias[o + 3]; }
+    if (residual) {
+        const float4 t = *reinterpret_cast<const float4*>(residual + (size_t)b * res_bs + (size_t)r * N + o);
+        v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+    }
+    v.x = mn_apply_act(v.x, act) * gain; v.y = mn_apply_act(v.y, act) * gain; v.z = mn_apply_act(v.z, act) * gain; v.w = mn_apply_act(v.w, act) * gain;
+    *reinterpret_cast<float4*>(y + i4) = v;
 }
 
 // 32x32 smem-tiled transposes between [C][HW] and [HW][C] per sample.
@@ -307,19 +359,22 @@ extern "C" int mn_layernorm(const float* x, float* y, const float* gamma, const 
     return MN_OK;
 }
 
-extern "C" int mn_linear_small_m_ex(const float* x, long long x_row_stride, long long x_batch_stride, int x_seg_len, long long x_seg_stride,
-                                    const float* w, const float* bias, const float* residual, long long res_batch_stride, float* y,
-                                    int batches, int M, int K, int N, int act, float gain, void* stream) {
-    MN_REQUIRE(x && w && y && M > 0 && M <= 64 && K > 0 && K % 32 == 0 && N > 0 && N % 16 == 0 && batches > 0 && batches <= 65535,
+static int linear_small_m_impl(const float* x, long long x_row_stride, long long x_batch_stride, int x_seg_len, long long x_seg_stride,
+                               const float* w, const float* bias, const float* residual, long long res_batch_stride, float* y,
+                               int batches, int M, int K, int N, int act, float gain, float* ws, long long ws_bytes, void* stream) {
+    MN_REQUIRE(x && w && y && M > 0 && M <= 64 && K > 0 && K % 32 == 0 && N > 0 && N % 16 == 0 && batches > 0 && batches <= 8192,
                "mn_linear_small_m: needs M<=64, K%32==0, N%16==0");
     MN_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0, "mn_linear_small_m: x, w must be 16-byte aligned");
     MN_REQUIRE(x_seg_len > 0 && x_seg_len % 32 == 0 && K % x_seg_len == 0 && (x_row_stride & 3) == 0 && (x_seg_stride & 3) == 0 && (x_batch_stride & 3) == 0,
                "mn_linear_small_m: gathered x needs 32-float segments and 16-byte aligned strides");
-    LinArgs a{x, x_row_stride, x_batch_stride, x_seg_len, x_seg_stride, w, bias, residual, res_batch_stride, y, M, K, N, act, gain};
+    LinArgs a{x, x_row_stride, x_batch_stride, x_seg_len, x_seg_stride, w, bias, residual, res_batch_stride, y, M, K, N, act, gain, 1};
     // tile: all rows x 16 columns (many small CTAs: these layers are latency bound and 64-row x 64-column tiles leave too few
-    // warps per SM -- measured 39 vs 14 us for 64x512x1024); 64 columns only for the <= 16-row layers with many columns
-    // (the generator's 17 modulation FCs as one 16x512x7168 GEMM: 18 vs 30 us).
-    const bool wide = (M <= 16 && N >= 1024);
+    // warps per SM -- measured 39 vs 14 us for 64x512x1024); 64 columns for the <= 16-row layers with many columns
+    // (the generator's 17 modulation FCs as one 16x512x7168 GEMM: 18 vs 30 us) and for DEEP-K layers (the TextViT patch embedding,
+    // K = 32768: with 16-column tiles every one of the N/16 column tiles re-reads the whole 8.4 MB activation matrix -- 268 MB of
+    // L2->SMEM traffic next to 67 MB of weights, measured 150 us = 0.44 TB/s; 64-column tiles read it N/64 times).
+    const bool deep = K >= 8192 && N % 64 == 0;
+    const bool wide = (M <= 16 && N >= 1024) || deep;
     const int tiles = mn_cdiv(N, wide ? 64 : 16) * batches;
     // K slices (one cluster, <= 8 CTAs): spread a small layer over ~one CTA per SM, a long K over ~two
     const int sms = mn_num_sms(), chunks = K / 32;
@@ -329,6 +384,18 @@ extern "C" int mn_linear_small_m_ex(const float* x, long long x_row_stride, long
     static int force_ks = -1;                            // developer override: MN_LIN_KS=1|2|4|8
     if (force_ks < 0) { const char* e = getenv("MN_LIN_KS"); force_ks = e ? atoi(e) : 0; }
     if (force_ks > 0) { ks = force_ks; while (ks > 1 && chunks / ks < 1) ks /= 2; }
+    // outer K slices beyond the cluster limit (deep K, few tiles): raw partial tiles go to the caller's workspace, a second
+    // kernel adds them in slice order and runs the epilogue (deterministic; no atomics)
+    int ko = 1;
+    if (deep && ws) {
+        while (ko < 8 && tiles * ks * ko * 2 <= 4 * sms && chunks / (ks * ko * 2) >= 8 &&
+               (long long)(ko * 2) * batches * M * N * 4 <= ws_bytes) ko *= 2;
+    }
+    static int force_ko = -1;
+    if (force_ko < 0) { const char* e = getenv("MN_LIN_KO"); force_ko = e ? atoi(e) : 0; }
+    if (force_ko > 0 && ws && (long long)force_ko * batches * M * N * 4 <= ws_bytes && chunks / (ks * force_ko) >= 1) ko = force_ko;
+    a.ko = ko;
+    if (ko > 1) a.y = ws;
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
     const int mt = M <= 16 ? 16 : (M <= 32 ? 32 : 64);
@@ -336,7 +403,29 @@ extern "C" int mn_linear_small_m_ex(const float* x, long long x_row_stride, long
     else e = mt == 16 ? launch_linear<16, 16>(a, batches, ks, st) : (mt == 32 ? launch_linear<32, 16>(a, batches, ks, st) : launch_linear<64, 16>(a, batches, ks, st));
     MN_CUDA_CHECK(e);
     MN_LAUNCH_CHECK();
+    if (ko > 1) {
+        const long long slice = (long long)batches * M * N;
+        MN_CUDA_CHECK((mn_launch(linear_ko_reduce_kernel, dim3((unsigned)mn_cdiv64(slice / 4, 256)), dim3(256), 0, st, (const float*)ws, ko, slice, bias,
+                                 residual, res_batch_stride, y, M, N, act, gain)));
+        MN_LAUNCH_CHECK();
+    }
     return MN_OK;
+}
+
+extern "C" int mn_linear_small_m_ex(const float* x, long long x_row_stride, long long x_batch_stride, int x_seg_len, long long x_seg_stride,
+                                    const float* w, const float* bias, const float* residual, long long res_batch_stride, float* y,
+                                    int batches, int M, int K, int N, int act, float gain, void* stream) {
+    return linear_small_m_impl(x, x_row_stride, x_batch_stride, x_seg_len, x_seg_stride, w, bias, residual, res_batch_stride, y, batches, M, K, N,
+                               act, gain, nullptr, 0, stream);
+}
+
+extern "C" int mn_linear_small_m_ws(const float* x, long long x_row_stride, long long x_batch_stride, int x_seg_len, long long x_seg_stride,
+                                    const float* w, const float* bias, const float* residual, long long res_batch_stride, float* y,
+                                    int batches, int M, int K, int N, int act, float gain, float* workspace, long long workspace_bytes,
+                                    void* stream) {
+    MN_REQUIRE(!workspace || (((uintptr_t)workspace & 15) == 0 && N % 4 == 0), "mn_linear_small_m_ws: workspace alignment");
+    return linear_small_m_impl(x, x_row_stride, x_batch_stride, x_seg_len, x_seg_stride, w, bias, residual, res_batch_stride, y, batches, M, K, N,
+                               act, gain, workspace, workspace_bytes, stream);
 }
 
 extern "C" int mn_linear_small_m(const float* x, const float* w, const float* bias, const float* residual, float* y,
@@ -355,10 +444,13 @@ extern "C" int mn_token_mix(const float* x, const float* gamma, const float* bet
 extern "C" int mn_attention(const float* qkv, float* out, int B, int S, int heads, int dh, float scale, void* stream) {
     MN_REQUIRE(qkv && out && B > 0 && heads > 0, "mn_attention: bad args");
     MN_REQUIRE(S > 0 && S <= 64 && dh == 64, "mn_attention: needs S<=64 and dh==64 (got S=%d dh=%d)", S, dh);
-    constexpr int kSmem = (64 * 64 * 2 + 64 * 65 * 2) * (int)sizeof(float);
+    MN_REQUIRE(((uintptr_t)qkv & 15) == 0, "mn_attention: qkv must be 16-byte aligned");
+    constexpr int QC = 8;
+    constexpr int kSmem = (QC * 64 + 64 * 68 + 64 * 64 + QC * 68) * (int)sizeof(float);
     static unsigned long long smem_done = 0;
-    MN_CUDA_CHECK(mn_ensure_dyn_smem(attention_kernel, kSmem, &smem_done));
-    MN_CUDA_CHECK((mn_launch(attention_kernel, dim3(B * heads), dim3(256), kSmem, (cudaStream_t)stream, qkv, out, S, heads, scale)));
+    MN_CUDA_CHECK(mn_ensure_dyn_smem(attention_kernel<QC>, kSmem, &smem_done));
+    const int nch = mn_cdiv(S, QC);
+    MN_CUDA_CHECK((mn_launch(attention_kernel<QC>, dim3(B * heads * nch), dim3(128), kSmem, (cudaStream_t)stream, qkv, out, S, heads, nch, scale)));
     MN_LAUNCH_CHECK();
     return MN_OK;
 }

@@ -399,7 +399,8 @@ class ResTextBlockV2(nn.Module):
 
 def _res_block(pk, x, valid_w=None):
     """GN -> swish -> conv -> GN -> swish -> conv (+ 1x1 skip), reference networks.py:506-516."""
-    # GroupNorm statistics are a separate (read-only) pass; normalise + swish is fused into the consuming conv's operand stage
+    # GroupNorm statistics are a separate (read-only) pass; normalise + swish runs as mn_groupnorm_apply before the conv unless
+    # ops.FUSE_GN routes it into the tcgen05 kernel's operand-split stage (measured slower with 4 split warps; off by default)
     mr1 = ops.groupnorm_stats(x, valid_w=valid_w)
     h = ops.conv2d(x, pk["c1"][0], 3, 3, pad=(1, 1), bias=pk["c1"][1], valid_w=valid_w, gn=(mr1,) + tuple(pk["n1"]))
     mr2 = ops.groupnorm_stats(h, valid_w=valid_w)

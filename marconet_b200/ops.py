@@ -282,6 +282,31 @@ class calibration:
         return out
 
 
+TC_FALLBACKS = {}      # shape key -> (layer name, GFLOP, reason): convs that a tensor-core default ran on the fp32 CUDA-core kernel
+
+
+def _note_fallback(cw, key, flop, p):
+    """A tensor-core precision was the default but this conv runs on the exact fp32 kernel (unsupported geometry: Cin/Cout not
+    multiples of 64, stride != 1, tiny launch ...).  Logged ONCE per shape so that a checkpoint with different channel counts does
+    not quietly run 6x slower; ``ops.TC_FALLBACKS`` keeps the list, bench.py reports it."""
+    if key in TC_FALLBACKS:
+        return
+    if flop < TC_MIN_FLOP:
+        reason = f"below TC_MIN_FLOP ({flop / 1e6:.1f} MFLOP)"
+    elif cw is None or not cw.tc_capable():
+        reason = "Cin or Cout is not a multiple of 64"
+    elif key[7] != (1, 1):
+        reason = "stride != 1"
+    else:
+        lib = _lib.load()
+        lib.mn_conv2d_tc_supported(ctypes.byref(p))           # fills mn_last_error() with the kernel's own reason
+        reason = lib.mn_last_error().decode(errors="replace") or "unsupported geometry"
+    name = cw.name if cw is not None else "unnamed"
+    TC_FALLBACKS[key] = (name, flop / 1e9, reason)
+    import logging
+    logging.getLogger("marconet_b200").info("conv %s %s runs on the fp32 CUDA-core kernel: %s", name, key, reason)
+
+
 FUSE_GN = _os.environ.get("MN_FUSE_GN", "0") == "1"
 TC_MIN_FLOP = 3.0e7    # tiny launches are latency-bound either way and stay on the exact fp32 path
 
@@ -359,6 +384,7 @@ def conv2d(x, w, kh, kw, stride=(1, 1), pad=(0, 0), bias=None, out_scale=None, r
                                + lib.mn_last_error().decode(errors="replace"))
         else:
             prec = PREC_FP32_SIMT
+            _note_fallback(cw, (n, h, wd, cin, cout, kh, kw, stride), 2.0 * n * oh * ow * cout * kh * kw * cin, p)
     p.precision = prec
     if gn is not None and not gn_fused:      # no fused kernel for this layer: normalise into a temporary first
         xg = groupnorm_apply(x, gn[0], gn[1], gn[2], valid_w=valid_w)
@@ -418,9 +444,10 @@ def patch_embed(feat, w, bias, pe):
     if k != 64 * c or t > 64 or tuple(pe.shape) != (t, d):
         raise RuntimeError("patch_embed: weight / positional embedding do not match the feature map")
     y = torch.empty((b * t, d), dtype=torch.float32, device=feat.device)
-    _lib.check(_lib.load().mn_linear_small_m_ex(_ptr(feat), 8 * c, 8 * fw * c, 8 * c, fw * c, _ptr(w), _ptr(bias), _ptr(pe), 0, _ptr(y),
-                                                b, t, k, d, ACT_NONE, 1.0, _stream()), "mn_linear_small_m_ex")
-    LAUNCHES += 1
+    ws = workspace(feat.device)         # outer K slices (deep K, few column tiles): partial tiles + a deterministic reduce kernel
+    _lib.check(_lib.load().mn_linear_small_m_ws(_ptr(feat), 8 * c, 8 * fw * c, 8 * c, fw * c, _ptr(w), _ptr(bias), _ptr(pe), 0, _ptr(y),
+                                                b, t, k, d, ACT_NONE, 1.0, _ptr(ws), ws.numel() * 4, _stream()), "mn_linear_small_m_ws")
+    LAUNCHES += 2
     return y
 
 

@@ -93,3 +93,57 @@ def _generate_pipelined(generator, styles, labels, group, world, rank, chunks):
     for w, _ in works:
         w.wait()
     return tuple(buf.permute(0, 3, 1, 2) for buf in full)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Owner-only exchange (round 2).  The all-gather above gives EVERY rank ALL priors (6 MiB per character: 6.6 GB received per rank
+# for 1024 characters at 8 GPUs, measured 8.9 ms at the NVLink all-gather limit, after the compute) although only the rank that
+# runs the SR decoder of a line ever reads that line's priors (reference consumer: networks.py:442-445, 475-478).  Here lines are
+# owned by ranks (contiguous blocks), characters are generated BLOCK-CYCLICALLY -- rank r generates the r-th sub-block of every
+# owner's characters -- and one all-to-all delivers each sub-block to its owner, where it lands in natural character order:
+# (world-1)/world of 6 MiB per OWNED character crosses NVLink instead of (world-1) x 6 MiB.
+# ---------------------------------------------------------------------------------------------------------------------
+def owner_blocks(n_chars, world):
+    """Block-cyclic plan for n_chars = world*world*sub characters.  Returns sub; owner o owns [o*world*sub, (o+1)*world*sub),
+    and rank r generates, for every owner o, characters [o*world*sub + r*sub, +sub)."""
+    if n_chars % (world * world) != 0:
+        raise ValueError(f"owner exchange needs the character count ({n_chars}) to be a multiple of world^2 = {world * world}")
+    return n_chars // (world * world)
+
+
+def generate_priors_for_owners(generator, styles, labels, group=None, keep=(1, 2), exchange=True):
+    """Character-sharded TSPGAN with owner-only exchange.  ``styles`` / ``labels`` describe ALL characters (identical on every
+    rank); returns the priors of the characters this rank OWNS (``[rank*n/world, (rank+1)*n/world)``, natural order) as a tuple
+    of the generator outputs selected by ``keep`` (default: fea64, fea32 -- what the SR decoder reads; the 128-px image stays
+    where it was generated), each a channels_last NCHW-shaped view like the generator's own outputs.
+
+    exchange=False skips the all-to-all and returns the LOCALLY GENERATED characters instead (bench: compute-only time).
+    One NCCL all_to_all_single per kept tensor, equal splits of ``sub`` characters."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n = labels.shape[0]
+    if world == 1:
+        outs = generator(styles, labels, None)
+        return tuple(outs[k] for k in keep)
+    sub = owner_blocks(n, world)
+    idx = torch.cat([torch.arange(o * world * sub + rank * sub, o * world * sub + (rank + 1) * sub) for o in range(world)])
+    idx_s = idx.to(styles.device)
+    outs = generator(styles.index_select(0, idx_s), labels.index_select(0, idx.to(labels.device)), None)
+    result = []
+    for k in keep:
+        o = outs[k]
+        cl = o.dim() == 4 and o.permute(0, 2, 3, 1).is_contiguous()
+        local = o.permute(0, 2, 3, 1) if cl else o.contiguous()            # [world*sub, ...]: block d goes to owner d
+        if not exchange:
+            result.append(o)
+            continue
+        recv = torch.empty_like(local)                                      # block s arrives from rank s = sub-block s of my range
+        dist.all_to_all_single(recv, local.contiguous(), group=group)
+        result.append(recv.permute(0, 3, 1, 2) if cl else recv)
+    return tuple(result)
+
+
+def exchange_bytes_per_rank(n_chars, world, bytes_per_char=6 * (1 << 20)):
+    """Bytes each rank sends (= receives) in generate_priors_for_owners vs in the all-gather variant."""
+    owned = n_chars // world
+    return dict(all_to_all=owned * bytes_per_char * (world - 1) // world, all_gather=(n_chars - owned) * bytes_per_char)

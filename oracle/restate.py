@@ -103,7 +103,7 @@ def textvit(sd, feat, prefix="transformer."):
     # Rearrange 'b c (h p1) (w p2) -> b h w (p1 p2 c)'  (textvit_arch.py:32-35)
     x0 = feat.reshape(b, c, h, p1, w, p2).permute(0, 2, 4, 3, 5, 1).reshape(b, h, w, p1 * p2 * c)
     x0 = F.linear(x0, sd[prefix + "to_patch_embedding.1.weight"], sd[prefix + "to_patch_embedding.1.bias"])
-    pe = posemb_sincos_2d(h, w, x0.shape[-1], x0.dtype)
+    pe = posemb_sincos_2d(h, w, x0.shape[-1], x0.dtype).to(x0.device)
     x = x0.reshape(b, h * w, -1) + pe
     t = prefix + "transformer."
     for i in range(2):

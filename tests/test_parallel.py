@@ -59,3 +59,45 @@ def test_char_sharded_generation_world2_gloo(n_chars):
     ok = mp.get_context("spawn").Array("i", [0, 0])
     mp.spawn(_worker, args=(2, port, n_chars, ok), nprocs=2, join=True)
     assert list(ok) == [1, 1]
+
+
+def _owner_worker(rank, world, port, n_chars, ok):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from marconet_b200.parallel import exchange_bytes_per_rank, generate_priors_for_owners
+        g = torch.Generator().manual_seed(9)
+        styles = torch.randn(n_chars, 16, generator=g)
+        labels = torch.randint(0, 100, (n_chars, 1), generator=g)
+        full = _fake_generator(styles, labels, None)
+        own = slice(rank * n_chars // world, (rank + 1) * n_chars // world)
+        f64, f32 = generate_priors_for_owners(_fake_generator, styles, labels)
+        good = torch.equal(f64, full[1][own]) and torch.equal(f32, full[2][own])          # natural order, owned characters only
+        good &= f64.permute(0, 2, 3, 1).is_contiguous()
+        img, = generate_priors_for_owners(_fake_generator, styles, labels, keep=(0,))
+        good &= torch.equal(img, full[0][own])
+        loc = generate_priors_for_owners(_fake_generator, styles, labels, exchange=False)
+        good &= loc[0].shape[0] == n_chars // world
+        b = exchange_bytes_per_rank(n_chars, world, bytes_per_char=10)
+        good &= b["all_to_all"] * world == b["all_gather"]
+        ok[rank] = 1 if good else 0
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_chars", [4, 16])
+def test_owner_only_exchange_world2_gloo(n_chars):
+    """Block-cyclic generation + all-to-all: every rank ends up with exactly its own lines' priors, in order."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ok = mp.get_context("spawn").Array("i", [0, 0])
+    mp.spawn(_owner_worker, args=(2, port, n_chars, ok), nprocs=2, join=True)
+    assert list(ok) == [1, 1]
+
+
+def test_owner_blocks_rejects_ragged_counts():
+    from marconet_b200.parallel import owner_blocks
+    assert owner_blocks(1024, 8) == 16
+    with pytest.raises(ValueError):
+        owner_blocks(100, 8)
