@@ -49,16 +49,24 @@ struct Tc2Geom {
     int tiles_w, tiles_h, tiles_n, m_tiles, m_groups, n_tiles;
     int cblocks, taps, KW, ph, pw;
     int ksplit, cbps;   // split-K over channel blocks for layers with too few tiles: work = (tile, k-slice), cbps channel blocks each
-    int bstages, cs;
+    int bstages, cs, cg;
     const float* wscale;
     int prec;
 };
 
-template <int NT, bool GN>
+// CG = 2: the two CTAs of a cluster form ONE tcgen05 CTA pair (cta_group::2): a single MMA covers M = 256 pixels (128 per CTA,
+// each CTA's A operand in its own TMEM) x NT channels, and each CTA keeps only ITS HALF of every weight tile in shared memory
+// (NT/2 rows; no multicast).  Why: with cta_group::1 the tensor core reads B (4 KB per 64-cycle MMA = 64 B/clk) from the same
+// shared-memory port that the TMEM-feed warps read the halo through (32 KB per k-block = 42 B/clk) and the split warps work
+// in -- ~120 of the port's 128 B/clk, which is what held the kernel at ~73 % of the tensor pipe although the MMA stream alone
+// issues at 95-100 % (tools/mma_probe2.cu).  The pair halves the B reads per SM.  Only the leader CTA (cluster rank 0) issues MMAs;
+// its barriers collect the peer's TMA bytes (BF), feed-warp arrivals (CD) and epilogue arrivals (ACCE) through DSMEM, and its
+// tcgen05.commit multicasts the stage-release / accumulator-full signals to both CTAs.
+template <int NT, bool GN, int CG>
 __global__ void __launch_bounds__(NUM_THREADS2, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
                 const __grid_constant__ CUtensorMap tmBlo, const ConvGeom g, const Tc2Geom t) {
-    constexpr int B_HALF = NT * 128;              // bytes of one (hi or lo) weight tile
+    constexpr int B_HALF = (NT / CG) * 128;       // bytes of one (hi or lo) weight tile held by this CTA
     constexpr int B_STAGE = 2 * B_HALF;
     constexpr int A_COL0 = 2 * NT;                // TMEM: D [0,NT), Dc [NT,2NT), A stage s at 2NT+64s (hi) / +32 (lo)
     static_assert(2 * NT + A_STAGES * 64 <= TMEM_COLS2, "TMEM budget");
@@ -99,13 +107,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBhi) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBlo) : "memory");
         for (int s = 0; s < 2; ++s) { mbar_init(bar(I_HF + s), 1); mbar_init(bar(I_HE + s), 128); mbar_init(bar(I_SD + s), 128); }
-        for (int s = 0; s < MAX_BSTAGES; ++s) { mbar_init(bar(I_BF + s), 1); mbar_init(bar(I_BE + s), cs); }
-        for (int s = 0; s < A_STAGES; ++s) { mbar_init(bar(I_CD + s), 128); mbar_init(bar(I_AE + s), 1); }
+        for (int s = 0; s < MAX_BSTAGES; ++s) { mbar_init(bar(I_BF + s), 1); mbar_init(bar(I_BE + s), CG == 2 ? 1 : cs); }
+        // CG = 2: one elected arrival per feed / epilogue warp of BOTH CTAs lands on the leader's barrier (4 local + 4 remote)
+        for (int s = 0; s < A_STAGES; ++s) { mbar_init(bar(I_CD + s), CG == 2 ? 8 : 128); mbar_init(bar(I_AE + s), 1); }
         mbar_init(bar(I_ACCF), 1);
-        mbar_init(bar(I_ACCE), 128);
+        mbar_init(bar(I_ACCE), CG == 2 ? 8 : 128);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS2);
+    if (warp == 1) { if (CG == 2) tmem_alloc_cg2(smem_u32(tmem_slot), TMEM_COLS2); else tmem_alloc(smem_u32(tmem_slot), TMEM_COLS2); }
     tc_fence_before();
     __syncthreads();
     if (cs > 1) cluster_sync_all();
@@ -129,7 +138,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         // =========================== weight (B) producer (whole warp converged, one elected lane issues) ===========================
         uint32_t s = 0, ph = 0;
         const int rows = NT / cs;
-        const uint32_t dst0 = smem_base + off_b + crank * rows * 128;
+        const uint32_t dst0 = smem_base + off_b + (CG == 2 ? 0u : crank * rows * 128);
         for (int work = cluster_id; work < total_work; work += num_clusters) {
             const int row0 = work_nt(work) * NT + (int)crank * rows;
             const int cb0 = work_ks(work) * t.cbps;
@@ -137,12 +146,19 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 for (int tap = 0; tap < t.taps; ++tap) {
                     mbar_wait(bar(I_BE + s), ph ^ 1);
                     if (elect_one_sync()) {
-                        mbar_expect_tx(bar(I_BF + s), B_STAGE);
                         const uint32_t dst = dst0 + s * B_STAGE;
-                        if (cs > 1) {
+                        if (CG == 2) {
+                            // this CTA's half of the tile into its own smem; bytes of BOTH halves are counted on the LEADER's barrier
+                            if (crank == 0) mbar_expect_tx(bar(I_BF + s), 2 * B_STAGE);
+                            const uint32_t lbar = mapa_u32(bar(I_BF + s), 0);
+                            tma_load_3d_cg2(&tmBhi, lbar, dst, cb * KB, row0, tap);
+                            tma_load_3d_cg2(&tmBlo, lbar, dst + B_HALF, cb * KB, row0, tap);
+                        } else if (cs > 1) {
+                            mbar_expect_tx(bar(I_BF + s), B_STAGE);
                             tma_load_3d_mc(&tmBhi, bar(I_BF + s), dst, cb * KB, row0, tap, cmask);
                             tma_load_3d_mc(&tmBlo, bar(I_BF + s), dst + B_HALF, cb * KB, row0, tap, cmask);
                         } else {
+                            mbar_expect_tx(bar(I_BF + s), B_STAGE);
                             tma_load_3d(&tmBhi, bar(I_BF + s), dst, cb * KB, row0, tap);
                             tma_load_3d(&tmBlo, bar(I_BF + s), dst + B_HALF, cb * KB, row0, tap);
                         }
@@ -238,7 +254,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             drain(0, false);
             if (HALVES > 1) drain(1, true);
             tc_fence_before();
-            mbar_arrive(bar(I_ACCE));                            // accumulators fully read: the MMA warp may start the next tile
+            if (CG == 2) {                                       // one arrival per warp, on the LEADER's barrier (it issues the pair's MMAs)
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(mapa_u32(bar(I_ACCE), 0));
+            } else {
+                mbar_arrive(bar(I_ACCE));                        // accumulators fully read: the MMA warp may start the next tile
+            }
 #pragma unroll 1
             for (int half = 0; half < HALVES; ++half) {
                 if (half == 1) {
@@ -362,9 +383,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (prev_work >= 0) epilogue(prev_work);
         conv_range_report(g, amax, t.prec == MN_PREC_F16X3_TC || t.prec == MN_PREC_F16X1_TC);
     } else if (warp == 1) {
+      if (CG == 1 || crank == 0) {
         // =========================== MMA issuer (whole warp converged, one elected lane issues) ===========================
         const uint32_t fmt = (t.prec == MN_PREC_BF16X3_TC) ? 1u : 0u;
-        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)((128 * CG) >> 4) << 24);
         const bool three = t.prec != MN_PREC_F16X1_TC;
         const int num_kb = t.cbps * t.taps;
         const uint64_t desc_hi0 = make_b_desc(smem_base + off_b);           // stage 0, hi plane, k-step 0
@@ -382,23 +404,37 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     const uint32_t a_hi = tmem_base + A_COL0 + as * 64;
 #pragma unroll
                     for (int j = 0; j < KB / 16; ++j) {
-                        tc_mma_ts(tmem_base, a_hi + j * 8, dh0 + 2 * j, idesc, (kb | j) != 0);
-                        if (three) {
-                            tc_mma_ts(tmem_base + NT, a_hi + j * 8, dl0 + 2 * j, idesc, (kb | j) != 0);
-                            tc_mma_ts(tmem_base + NT, a_hi + 32 + j * 8, dh0 + 2 * j, idesc, 1);
+                        if (CG == 2) {
+                            tc_mma_ts_cg2(tmem_base, a_hi + j * 8, dh0 + 2 * j, idesc, (kb | j) != 0);
+                            if (three) {
+                                tc_mma_ts_cg2(tmem_base + NT, a_hi + j * 8, dl0 + 2 * j, idesc, (kb | j) != 0);
+                                tc_mma_ts_cg2(tmem_base + NT, a_hi + 32 + j * 8, dh0 + 2 * j, idesc, 1);
+                            }
+                        } else {
+                            tc_mma_ts(tmem_base, a_hi + j * 8, dh0 + 2 * j, idesc, (kb | j) != 0);
+                            if (three) {
+                                tc_mma_ts(tmem_base + NT, a_hi + j * 8, dl0 + 2 * j, idesc, (kb | j) != 0);
+                                tc_mma_ts(tmem_base + NT, a_hi + 32 + j * 8, dh0 + 2 * j, idesc, 1);
+                            }
                         }
                     }
-                    tc_commit(bar(I_AE + as));
-                    if (cs > 1) tc_commit_mc(bar(I_BE + bs), cmask);
-                    else tc_commit(bar(I_BE + bs));
+                    if (CG == 2) {
+                        tc_commit_mc_cg2(bar(I_AE + as), cmask);
+                        tc_commit_mc_cg2(bar(I_BE + bs), cmask);
+                    } else {
+                        tc_commit(bar(I_AE + as));
+                        if (cs > 1) tc_commit_mc(bar(I_BE + bs), cmask);
+                        else tc_commit(bar(I_BE + bs));
+                    }
                 }
                 __syncwarp();
                 if (++as == A_STAGES) { as = 0; aph ^= 1; }
                 if (++bs == (uint32_t)BS) { bs = 0; bph ^= 1; }
             }
-            if (elect_one_sync()) tc_commit(bar(I_ACCF));
+            if (elect_one_sync()) { if (CG == 2) tc_commit_mc_cg2(bar(I_ACCF), cmask); else tc_commit(bar(I_ACCF)); }
             __syncwarp();
         }
+      }
     } else {
         // =========================== TMEM feed: shifted rows of the split halo -> A operand ===========================
         const int q = warp & 3;
@@ -437,7 +473,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     for (int c = 0; c < 4; ++c) tc_st8(a_dst + 32 + c * 8, lo + c * 8);
                     tc_wait_st();
                     tc_fence_before();
-                    mbar_arrive(bar(I_CD + as));
+                    if (CG == 2) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(mapa_u32(bar(I_CD + as), 0));
+                    } else {
+                        mbar_arrive(bar(I_CD + as));
+                    }
                     if (++as == A_STAGES) { as = 0; aph ^= 1; }
                 }
                 mbar_arrive(bar(I_HE + hs));         // all taps of this channel block have been read
@@ -451,7 +492,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (cs > 1) cluster_sync_all();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS2);
+        if (CG == 2) tmem_dealloc_cg2(tmem_base, TMEM_COLS2); else tmem_dealloc(tmem_base, TMEM_COLS2);
     }
 }
 
@@ -528,20 +569,24 @@ Tc2Plan plan_tc2(const ConvGeom& g) {
         if (t.ksplit > 1 && (!g.ws || g.gn_mr || (g.Cout & 3))) t.ksplit = 1;
     }
     t.cbps = t.cblocks / t.ksplit;
+    // cta_group::2 pairs (see the kernel): default whenever the cluster has 2 CTAs; MN_TC_CG=1 forces the cta_group::1 + multicast path
+    static int force_cg = -1;
+    if (force_cg < 0) { const char* e = getenv("MN_TC_CG"); force_cg = e ? atoi(e) : 0; }
+    t.cg = (t.cs == 2 && force_cg != 1) ? 2 : 1;
     const int fixed = 2 * t.halo_stage_bytes + STG_BYTES + 1024 + 512 + 256 + 1024;
-    int bs = (SMEM_LIMIT - fixed) / (2 * p.NT * 128);
+    int bs = (SMEM_LIMIT - fixed) / (2 * (p.NT / t.cg) * 128);
     if (bs > MAX_BSTAGES) bs = MAX_BSTAGES;
     if (bs < 2) return fail("not enough shared memory for 2 weight stages");
     t.bstages = bs;
-    p.smem = fixed + bs * 2 * p.NT * 128;
+    p.smem = fixed + bs * 2 * (p.NT / t.cg) * 128;
     p.ok = true;
     return p;
 }
 
-template <int NT, bool GN>
+template <int NT, bool GN, int CG>
 int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mbh, const CUtensorMap& mbl, const ConvGeom& g, const Tc2Plan& p, cudaStream_t st) {
     static unsigned long long smem_done = 0;
-    MN_CUDA_CHECK(mn_ensure_dyn_smem(conv_tc2_kernel<NT, GN>, SMEM_LIMIT, &smem_done));
+    MN_CUDA_CHECK(mn_ensure_dyn_smem(conv_tc2_kernel<NT, GN, CG>, SMEM_LIMIT, &smem_done));
     const Tc2Geom& t = p.t;
     const int total_work = t.m_groups * t.n_tiles * t.ksplit;
     int sms = mn_num_sms();
@@ -562,7 +607,7 @@ int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mbh, const CUtensorMap&
     static int pdl = -1;
     if (pdl < 0) { const char* e = getenv("MN_TC_PDL"); pdl = (e && e[0] == '0') ? 0 : 1; }
     cfg.attrs = attr; cfg.numAttrs = (pdl && mn_pdl_enabled()) ? 2 : 1;
-    MN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<NT, GN>, ma, mbh, mbl, g, t));
+    MN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<NT, GN, CG>, ma, mbh, mbl, g, t));
     return MN_OK;
 }
 
@@ -606,8 +651,13 @@ int mn_conv_tc2_launch(const ConvGeom& g, const void* w_hi, const void* w_lo, co
     t.wscale = w_scale + 1;
     t.prec = prec;
     int rc;
-    if (g.gn_mr) rc = p.NT == 128 ? launch_tc2<128, true>(ma, mbh, mbl, g, p, st) : launch_tc2<64, true>(ma, mbh, mbl, g, p, st);
-    else rc = p.NT == 128 ? launch_tc2<128, false>(ma, mbh, mbl, g, p, st) : launch_tc2<64, false>(ma, mbh, mbl, g, p, st);
+    if (t.cg == 2) {
+        if (g.gn_mr) rc = p.NT == 128 ? launch_tc2<128, true, 2>(ma, mbh, mbl, g, p, st) : launch_tc2<64, true, 2>(ma, mbh, mbl, g, p, st);
+        else rc = p.NT == 128 ? launch_tc2<128, false, 2>(ma, mbh, mbl, g, p, st) : launch_tc2<64, false, 2>(ma, mbh, mbl, g, p, st);
+    } else {
+        if (g.gn_mr) rc = p.NT == 128 ? launch_tc2<128, true, 1>(ma, mbh, mbl, g, p, st) : launch_tc2<64, true, 1>(ma, mbh, mbl, g, p, st);
+        else rc = p.NT == 128 ? launch_tc2<128, false, 1>(ma, mbh, mbl, g, p, st) : launch_tc2<64, false, 1>(ma, mbh, mbl, g, p, st);
+    }
     if (rc != MN_OK || t.ksplit == 1) return rc;
     ConvGeom gr = g;
     gr.splits = t.ksplit;

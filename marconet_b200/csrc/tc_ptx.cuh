@@ -141,6 +141,61 @@ __device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
                  : "memory");
 }
+// ---- cta_group::2 (one MMA over a CTA pair: M = 256, each CTA holds its 128 A rows in its own TMEM and HALF of B in its own smem) ----
+__device__ __forceinline__ void tmem_alloc_cg2(uint32_t smem_dst, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_mma_ts_cg2(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc_cg2(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+                 : "memory");
+}
+// shared::cluster address of `saddr` (a shared::cta address of THIS CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+// Arrive on an mbarrier of another CTA of the cluster.  Default semantics (release at CTA scope), like CUTLASS's ClusterBarrier:
+// with `.release.cluster` ptxas emits MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR in front of every arrive, which cost the TMEM-feed loop
+// ~15 % (measured).  What these arrivals publish is TMEM state, ordered by tcgen05.wait::st / tcgen05.fence::before_thread_sync.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA tile load of a CTA pair: data lands in THIS CTA's shared memory, the transaction bytes are signalled on an mbarrier that may
+// live in the peer (leader) CTA (`bar_cluster` is a shared::cluster address)
+__device__ __forceinline__ void tma_load_3d_cg2(const CUtensorMap* map, uint32_t bar_cluster, uint32_t dst, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+// wait with cluster-scope acquire: for barriers that also receive arrivals from the peer CTA
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    const long long t_start = clock64();
+    for (uint32_t it = 0; !done; ++it) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (!done && (it & 1023u) == 1023u && clock64() - t_start > 4000000000ll) __trap();
+    }
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 }  // namespace tcptx

@@ -414,6 +414,40 @@ def _two(pk, x, valid_w=None):
     return ops.conv2d(t, pk[1][0], 3, 3, pad=(1, 1), bias=pk[1][1], valid_w=valid_w)
 
 
+def _char_windows_np(arr, counts, width, half):
+    """Vectorised core of char_windows.  ``arr``: fp32 numpy [B, >= 2*n].  The centre is the fp32 product truncated toward zero,
+    exactly like ``(locs[b][2*c] * W).int()`` (numpy float32 array x np.float32 scalar is an fp32 multiply; astype(int32) truncates).
+    Returns (wins int32 [Nc,4] = (line, x1, x2, y1), valid int32 [Nc], owner int32 [B, W])."""
+    import numpy as np
+    nc = sum(counts)
+    wins = np.empty((nc, 4), np.int32)
+    valid = np.empty((nc,), np.int32)
+    owner = np.full((len(counts), width), -1, np.int32)
+    w32 = np.float32(width)
+    i = 0
+    for b, n in enumerate(counts):
+        if n == 0:
+            continue
+        cen = (arr[b, 0:2 * n:2].astype(np.float32, copy=False) * w32).astype(np.int32)
+        x1 = np.where(cen < half, 0, cen - half)
+        x2 = np.where(cen + half > width, width, cen + half)
+        wv = x2 - x1
+        bad = np.nonzero((wv <= 0) | (x1 >= width))[0]
+        if bad.size:
+            c = int(bad[0])
+            raise RuntimeError(f"character {c} of line {b}: empty window (centre {int(cen[c])}); the reference "
+                               f"fails on the empty slice at networks.py:443")
+        wins[i:i + n, 0] = b
+        wins[i:i + n, 1] = x1
+        wins[i:i + n, 2] = x2
+        wins[i:i + n, 3] = half - wv // 2            # wv > 0: floor division == the reference's trunc division
+        valid[i:i + n] = wv
+        for c in range(n):                           # program order: the last writer wins (networks.py:448,481)
+            owner[b, x1[c]:x2[c]] = i + c
+        i += n
+    return wins, valid, owner
+
+
 def char_windows(locs_host, counts, width, half):
     """Bit-exact restatement of the window integers of reference networks.py:426-441 / :460-474.
 
@@ -421,25 +455,8 @@ def char_windows(locs_host, counts, width, half):
     multiply, truncation).  Returns (windows [(line,x1,x2,y1)], valid widths, owner[b][x]) with
     "last character in program order wins" ownership (networks.py:448,481).
     """
-    wins, valid = [], []
-    owner = [[-1] * width for _ in counts]
-    i = 0
-    for b, n in enumerate(counts):
-        for c in range(n):
-            center = int((locs_host[b][2 * c] * width).int())
-            x1 = 0 if center < half else center - half
-            x2 = width if center + half > width else center + half
-            wv = x2 - x1
-            if wv <= 0 or x1 >= width:
-                raise RuntimeError(f"character {c} of line {b}: empty window (centre {center}); the reference "
-                                   f"fails on the empty slice at networks.py:443")
-            y1 = half - int(math.trunc(wv / 2))
-            wins.append((b, x1, x2, y1))
-            valid.append(wv)
-            for x in range(x1, x2):
-                owner[b][x] = i
-            i += 1
-    return wins, valid, owner
+    wins, valid, owner = _char_windows_np(locs_host.detach().to(torch.float32).contiguous().numpy(), counts, width, half)
+    return [tuple(int(v) for v in r) for r in wins], [int(v) for v in valid], owner.tolist()
 
 
 class TSPSRNet(_PackedModule):
@@ -512,11 +529,11 @@ class TSPSRNet(_PackedModule):
             win_dev, valid_dev, owner_dev = ops.char_windows(locs, self._line_first(counts, dev), counts, w, half, flag)
             vw = valid_dev                                # widths are not known on the host: always mask
         else:
-            wins, valid, owner = char_windows(locs, counts, w, half)
-            win_dev = torch.tensor(wins, dtype=torch.int32).to(dev)
-            valid_dev = torch.tensor(valid, dtype=torch.int32).to(dev)
-            owner_dev = torch.tensor(owner, dtype=torch.int32).to(dev)
-            vw = valid_dev if min(valid) < wp else None   # full-width windows need no masking
+            wins, valid, owner = _char_windows_np(locs.numpy() if isinstance(locs, torch.Tensor) else locs, counts, w, half)
+            win_dev = torch.from_numpy(wins).to(dev, non_blocking=True)
+            valid_dev = torch.from_numpy(valid).to(dev, non_blocking=True)
+            owner_dev = torch.from_numpy(owner).to(dev, non_blocking=True)
+            vw = valid_dev if int(valid.min()) < wp else None   # full-width windows need no masking
         fin = ops.adain_concat(prior, feat, win_dev, nc, wp)                         # [Nc,H,wp,2C]
         fuse = _res_block(pk[f"fuse{lvl}"], fin, vw)
         scale = _two(pk[f"conv_{lvl}_scale"], fuse, vw)
@@ -589,7 +606,7 @@ class TSPSRNet(_PackedModule):
         if ops.deferred_flag() is not None and locs.is_cuda:
             locs_host = locs.detach().float().contiguous()      # stays on the device; windows come from mn_char_windows
         else:
-            locs_host = locs.detach().to("cpu", torch.float32)
+            locs_host = locs.detach().to("cpu", torch.float32).contiguous()      # the one device->host round trip (reference: ~6 per character)
 
         s32 = _trunk if _trunk is not None else self._trunk(pk, lq)
 
