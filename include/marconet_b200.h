@@ -110,7 +110,7 @@ typedef struct {
      *   x_scale   power of two applied to the A operand before it is split and undone exactly in the epilogue (0 -> 1);
      *   x_absmax  optional DEVICE float: atomic max of |x * x_scale| over every element the kernel consumed (calibration);
      *   range_flag optional int32 the kernel STORES range_tag into when an operand element left the representable range
-     *             (fp16 modes: |x * x_scale| >= 65504; every mode: Inf / NaN).  May point to pinned host memory (plain store). */
+     *             (fp16 modes: |x * x_scale| >= 65504; every mode: Inf).  May point to pinned host memory (plain store). */
     float x_scale;
     float* x_absmax;
     int32_t* range_flag;

@@ -17,7 +17,8 @@ struct ConvGeom {
     float x_scale; float* x_absmax; int32_t* range_flag; int32_t range_tag;   // fp16-range management (tensor-core precisions)
 };
 
-// Range bookkeeping of the operand-split stage: `amax` is the running max of (bits(|x * x_scale|)) a thread has seen.
+// Range bookkeeping of the operand-split stage: `amax` = bits of the running fmaxf(|x * x_scale|) a thread has seen (fmaxf drops
+// NaNs: a NaN input is not flagged -- it reaches the output as NaN -- an Inf or an out-of-range finite value is).
 __device__ __forceinline__ void conv_range_report(const ConvGeom& g, uint32_t amax, bool fp16_mode) {
     if (!g.x_absmax && !g.range_flag) return;
     amax = __reduce_max_sync(0xffffffffu, amax);
@@ -92,6 +93,44 @@ __device__ __forceinline__ void conv_epilogue_vec4(const ConvGeom& g, int m, int
     if (g.y2) {
         if (g.y2_scale) {
             const float4 s = ldg4(g.y2_scale + (size_t)n * g.y2s_stride + o);
+            v.x *= s.x; v.y *= s.y; v.z *= s.z; v.w *= s.w;
+        }
+        *reinterpret_cast<float4*>(g.y2 + (size_t)m * g.y2_cs + o) = v;
+    }
+}
+
+// Specialised row epilogue of the tensor-core kernels: the activation is a template parameter (ACT < 0: runtime g.act, the
+// rarely used tanh / GELU / sigmoid heads) and the per-sample scale vectors may be passed in registers when every row of the tile
+// belongs to one sample.  The generic conv_epilogue_vec4 above costs ~120 SASS instructions per float4 (jump table on the
+// activation, predicated 64-bit address arithmetic for every optional operand); with four warps storing a 128x128 tile that was
+// ~10k cycles per tile -- more than the MMA time of a Cin <= 128 tile (ncu source page, profiles/r2_tc2_epilogue_before.txt).
+template <int ACT>
+__device__ __forceinline__ float mn_act_t(float v, int act) {
+    if (ACT == MN_ACT_NONE) return v;
+    if (ACT == MN_ACT_RELU) return fmaxf(v, 0.f);
+    if (ACT == MN_ACT_LRELU02) return v > 0.f ? v : 0.2f * v;
+    return mn_apply_act(v, act);
+}
+template <int ACT>
+__device__ __forceinline__ void conv_epilogue_row4(const ConvGeom& g, int m, int n, bool masked, int o, float4 v, const float4 bias4,
+                                                   bool have_os, const float4 os4, bool have_y2s, const float4 y2s4) {
+    if (g.out_scale) {
+        const float4 s = have_os ? os4 : ldg4(g.out_scale + (size_t)n * g.os_stride + o);
+        v.x *= s.x; v.y *= s.y; v.z *= s.z; v.w *= s.w;
+    }
+    v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+    if (g.residual) {
+        const size_t rm = g.res_bcast ? (size_t)(m - n * g.OH * g.OW) : (size_t)m;
+        const float4 r = ldg4(g.residual + rm * g.res_cs + o);
+        v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+    }
+    v.x = mn_act_t<ACT>(v.x, g.act) * g.gain; v.y = mn_act_t<ACT>(v.y, g.act) * g.gain;
+    v.z = mn_act_t<ACT>(v.z, g.act) * g.gain; v.w = mn_act_t<ACT>(v.w, g.act) * g.gain;
+    if (masked) v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g.y) *reinterpret_cast<float4*>(g.y + (size_t)m * g.y_cs + o) = v;
+    if (g.y2) {
+        if (g.y2_scale) {
+            const float4 s = have_y2s ? y2s4 : ldg4(g.y2_scale + (size_t)n * g.y2s_stride + o);
             v.x *= s.x; v.y *= s.y; v.z *= s.z; v.w *= s.w;
         }
         *reinterpret_cast<float4*>(g.y2 + (size_t)m * g.y2_cs + o) = v;

@@ -153,7 +153,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const bool bf = t.prec == MN_PREC_BF16X3_TC;
         const uint32_t mask = bf ? 0xFFFF0000u : 0xFFFFE000u;
         const float xs = g.x_scale;
-        uint32_t amax = 0;                     // range guard, see conv_common.cuh
+        float amax = 0.f;                      // range guard, see conv_common.cuh
         for (int kb = 0; kb < num_kb; ++kb) {
             const int s = kb % STAGES;
             const uint32_t ph = (kb / STAGES) & 1;
@@ -166,8 +166,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int j = 0; j < 8; ++j) {
                     float4 v = *reinterpret_cast<const float4*>(a_src + box * A_BOX_BYTES + ((j ^ (r & 7)) << 4));
                     v.x *= xs; v.y *= xs; v.z *= xs; v.w *= xs;
-                    amax = max(max(amax, __float_as_uint(v.x) & 0x7FFFFFFFu), max(__float_as_uint(v.y) & 0x7FFFFFFFu,
-                               max(__float_as_uint(v.z) & 0x7FFFFFFFu, __float_as_uint(v.w) & 0x7FFFFFFFu)));
+                    amax = fmaxf(fmaxf(amax, fabsf(v.x)), fmaxf(fabsf(v.y), fmaxf(fabsf(v.z), fabsf(v.w))));
                     const float h0 = __uint_as_float(__float_as_uint(v.x) & mask), h1 = __uint_as_float(__float_as_uint(v.y) & mask);
                     const float h2 = __uint_as_float(__float_as_uint(v.z) & mask), h3 = __uint_as_float(__float_as_uint(v.w) & mask);
                     const int c = box * 16 + j * 2;
@@ -190,7 +189,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_arrive(bar_conv(s));
         }
 
-        conv_range_report(g, amax, t.prec == MN_PREC_F16X3_TC || t.prec == MN_PREC_F16X1_TC);
+        conv_range_report(g, __float_as_uint(amax), t.prec == MN_PREC_F16X3_TC || t.prec == MN_PREC_F16X1_TC);
         // ---- epilogue ----
         mbar_wait(bar_acc, 0);
         tc_fence_after();

@@ -44,12 +44,17 @@ constexpr int STG_BYTES = 128 * STG_PITCH * 4;
 constexpr int TMEM_COLS2 = 512;
 constexpr int SMEM_LIMIT = 232448;          // 227 KB
 
+template <int A> struct ActTag { static constexpr int value = A; };
+
 struct Tc2Geom {
     int TW, TH, TN, HWd, HHt, halo_rows, box_bytes, halo_stage_bytes;
     int tiles_w, tiles_h, tiles_n, m_tiles, m_groups, n_tiles;
     int cblocks, taps, KW, ph, pw;
     int ksplit, cbps;   // split-K over channel blocks for layers with too few tiles: work = (tile, k-slice), cbps channel blocks each
     int bstages, cs, cg;
+    int hstages;        // depth of the halo ring (2, or 3 when shared memory allows: layers with <= 2 channel blocks per tile
+                        // otherwise stall every tile on the TMA latency of the next tile's second halo)
+    int epi_cb;         // the split warps run the epilogue of tile i after splitting this channel block of tile i+1
     const float* wscale;
     int prec;
 };
@@ -68,14 +73,19 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const __grid_constant__ CUtensorMap tmBlo, const ConvGeom g, const Tc2Geom t) {
     constexpr int B_HALF = (NT / CG) * 128;       // bytes of one (hi or lo) weight tile held by this CTA
     constexpr int B_STAGE = 2 * B_HALF;
-    constexpr int A_COL0 = 2 * NT;                // TMEM: D [0,NT), Dc [NT,2NT), A stage s at 2NT+64s (hi) / +32 (lo)
-    static_assert(2 * NT + A_STAGES * 64 <= TMEM_COLS2, "TMEM budget");
+    // TMEM: accumulator stage a: D [a*2NT, +NT), Dc [a*2NT+NT, +NT); A stage s at ACC_ST*2NT + 64s (hi) / +32 (lo).
+    // NT = 64 leaves room for TWO accumulator stages: the MMAs of tile i+1 start while the epilogue still drains tile i (the drain
+    // bubble is ~1k cycles against a 3.5k-cycle tile for the 64->64 layers at 128x2048).  NT = 128 fills TMEM with one.
+    constexpr int ACC_ST = (NT == 64) ? 2 : 1;
+    constexpr int A_COL0 = ACC_ST * 2 * NT;
+    static_assert(A_COL0 + A_STAGES * 64 <= TMEM_COLS2, "TMEM budget");
 
     extern __shared__ uint8_t smem_raw[];
     // keep the pointer in the shared address space (offset arithmetic on the array) so loads compile to LDS, not generic LD
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t smem_base = smem_u32(smem);
-    const uint32_t off_b = 2 * t.halo_stage_bytes;
+    const int HS = t.hstages;
+    const uint32_t off_b = HS * t.halo_stage_bytes;
     const uint32_t off_stg = off_b + t.bstages * B_STAGE;
     const uint32_t off_rowm = off_stg + STG_BYTES;
     const uint32_t off_gnp = off_rowm + 1024;
@@ -85,8 +95,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     float* gnp = reinterpret_cast<float*>(smem + off_gnp);       // gamma[64] | beta[64] of the current channel block (fused GroupNorm)
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + off_bars);
     // barrier indices
-    constexpr int I_HF = 0, I_HE = 2, I_BF = 4, I_BE = 4 + MAX_BSTAGES, I_CD = 4 + 2 * MAX_BSTAGES, I_AE = I_CD + A_STAGES,
-                  I_ACCF = I_AE + A_STAGES, I_ACCE = I_ACCF + 1, I_SD = I_ACCE + 1, N_BARS = I_SD + 2;
+    constexpr int MAX_HS = 3;
+    constexpr int I_HF = 0, I_HE = MAX_HS, I_BF = 2 * MAX_HS, I_BE = I_BF + MAX_BSTAGES, I_CD = I_BE + MAX_BSTAGES, I_AE = I_CD + A_STAGES,
+                  I_ACCF = I_AE + A_STAGES, I_ACCE = I_ACCF + 2, I_SD = I_ACCE + 2, N_BARS = I_SD + MAX_HS;
     auto bar = [&](int i) { return smem_u32(bars + i); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + N_BARS);
 
@@ -106,12 +117,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBhi) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBlo) : "memory");
-        for (int s = 0; s < 2; ++s) { mbar_init(bar(I_HF + s), 1); mbar_init(bar(I_HE + s), 128); mbar_init(bar(I_SD + s), 128); }
+        for (int s = 0; s < MAX_HS; ++s) { mbar_init(bar(I_HF + s), 1); mbar_init(bar(I_HE + s), 128); mbar_init(bar(I_SD + s), 128); }
         for (int s = 0; s < MAX_BSTAGES; ++s) { mbar_init(bar(I_BF + s), 1); mbar_init(bar(I_BE + s), CG == 2 ? 1 : cs); }
         // CG = 2: one elected arrival per feed / epilogue warp of BOTH CTAs lands on the leader's barrier (4 local + 4 remote)
         for (int s = 0; s < A_STAGES; ++s) { mbar_init(bar(I_CD + s), CG == 2 ? 8 : 128); mbar_init(bar(I_AE + s), 1); }
-        mbar_init(bar(I_ACCF), 1);
-        mbar_init(bar(I_ACCE), CG == 2 ? 8 : 128);
+        for (int a = 0; a < 2; ++a) { mbar_init(bar(I_ACCF + a), 1); mbar_init(bar(I_ACCE + a), CG == 2 ? 8 : 128); }
         fence_barrier_init();
     }
     if (warp == 1) { if (CG == 2) tmem_alloc_cg2(smem_u32(tmem_slot), TMEM_COLS2); else tmem_alloc(smem_u32(tmem_slot), TMEM_COLS2); }
@@ -184,7 +194,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     tma_load_4d(&tmA, bar(I_HF + hs), dst + t.box_bytes, cb * KB + 32, ox0 - t.pw, oy0 - t.ph, n0);
                 }
                 __syncwarp();
-                hs ^= 1; if (hs == 0) ph ^= 1;
+                if (++hs == (uint32_t)HS) { hs = 0; ph ^= 1; }
             }
         }
     } else if (warp >= 7) {
@@ -198,7 +208,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
         const float wscale = (t.wscale ? *t.wscale : 1.f) / g.x_scale;      // x_scale is a power of two: exact
         const float xs = g.x_scale;
-        uint32_t amax = 0;                                                  // max |x * x_scale| bits this thread has split (range guard)
+        float amax = 0.f;                                                   // max |x * x_scale| this thread has split (range guard)
         // The tensor core truncates (toward zero) every time it adds into the fp32 accumulator: measured mean shrink of the
         // main accumulator = 1.56e-8 per accumulation step, sign-symmetric, independent of K (tools/probe_tc_bias.py).  Undo the
         // expected shrink of D (K/16 steps); Dc is 2^-11 of the result and needs nothing.
@@ -218,7 +228,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 rowm[r] = ok ? (n * g.OH + oy) * g.OW + ox : -1;
                 rowm[128 + r] = ok ? (n | ((g.valid_w && ox >= g.valid_w[n]) ? (1 << 30) : 0)) : 0;
             }
-            mbar_wait(bar(I_ACCF), ecnt & 1);
+            const uint32_t acc_st = ACC_ST == 2 ? (ecnt & 1) : 0u, acc_ph = ACC_ST == 2 ? ((ecnt >> 1) & 1) : (ecnt & 1);
+            const uint32_t acc_addr = lane_addr + acc_st * 2 * NT;
+            mbar_wait(bar(I_ACCF + acc_st), acc_ph);
             ++ecnt;
             tc_fence_after();
             constexpr int HALVES = NT / STG_COLS;
@@ -227,10 +239,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                 for (int chunk = 0; chunk < STG_COLS / 16; ++chunk) {
                     uint32_t acc[16];
-                    tc_ld16(lane_addr + half * STG_COLS + chunk * 16, acc);
+                    tc_ld16(acc_addr + half * STG_COLS + chunk * 16, acc);
                     if (t.prec != MN_PREC_F16X1_TC) {
                         uint32_t cor[16];
-                        tc_ld16(lane_addr + NT + half * STG_COLS + chunk * 16, cor);
+                        tc_ld16(acc_addr + NT + half * STG_COLS + chunk * 16, cor);
                         tc_wait_ld();
 #pragma unroll
                         for (int i = 0; i < 16; ++i) acc[i] = __float_as_uint(fmaf(__uint_as_float(acc[i]), dfix, __uint_as_float(cor[i])) * wscale);
@@ -256,9 +268,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             tc_fence_before();
             if (CG == 2) {                                       // one arrival per warp, on the LEADER's barrier (it issues the pair's MMAs)
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(mapa_u32(bar(I_ACCE), 0));
+                if (lane == 0) mbar_arrive_cluster(mapa_u32(bar(I_ACCE + acc_st), 0));
             } else {
-                mbar_arrive(bar(I_ACCE));                        // accumulators fully read: the MMA warp may start the next tile
+                mbar_arrive(bar(I_ACCE + acc_st));               // accumulators fully read: the MMA warp may start the next tile
             }
 #pragma unroll 1
             for (int half = 0; half < HALVES; ++half) {
@@ -273,18 +285,43 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 {
                     const int col = (lane & 15) * 4;
                     const int o = nt_i * NT + half * STG_COLS + col;
-                    const float4 bias4 = g.bias ? ldg4(g.bias + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (t.ksplit > 1) {
+                        // raw partial sum of this k-slice; conv_splitk_reduce_kernel adds the slices and runs the epilogue
 #pragma unroll 4
-                    for (int i = 0; i < 16; ++i) {
-                        const int row = q * 32 + i * 2 + (lane >> 4);
-                        const int m = rowm[row];
-                        if (m >= 0) {
-                            const int nn = rowm[128 + row];
-                            const float4 u = *reinterpret_cast<const float4*>(stg + row * STG_PITCH + col);
-                            if (t.ksplit > 1)      // raw partial sum of this k-slice; conv_splitk_reduce_kernel adds the slices and runs the epilogue
-                                *reinterpret_cast<float4*>(g.ws + ((size_t)ks * g.M + m) * g.Cout + o) = u;
-                            else
-                                conv_epilogue_vec4(g, m, nn & 0x3FFFFFFF, (nn >> 30) != 0, o, u, bias4);
+                        for (int i = 0; i < 16; ++i) {
+                            const int row = q * 32 + i * 2 + (lane >> 4);
+                            const int m = rowm[row];
+                            if (m >= 0)
+                                *reinterpret_cast<float4*>(g.ws + ((size_t)ks * g.M + m) * g.Cout + o) =
+                                    *reinterpret_cast<const float4*>(stg + row * STG_PITCH + col);
+                        }
+                    } else {
+                        const float4 bias4 = g.bias ? ldg4(g.bias + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        // one sample per tile (every layer except the 4x4 .. 8x8 maps): its per-sample scale vectors are loaded once
+                        const bool one_n = t.TN == 1;
+                        float4 os4 = make_float4(1.f, 1.f, 1.f, 1.f), y2s4 = os4;
+                        if (one_n && n0 < g.N) {
+                            if (g.out_scale) os4 = ldg4(g.out_scale + (size_t)n0 * g.os_stride + o);
+                            if (g.y2 && g.y2_scale) y2s4 = ldg4(g.y2_scale + (size_t)n0 * g.y2s_stride + o);
+                        }
+                        auto rows = [&](auto tag) {
+                            constexpr int ACT = decltype(tag)::value;
+#pragma unroll 4
+                            for (int i = 0; i < 16; ++i) {
+                                const int row = q * 32 + i * 2 + (lane >> 4);
+                                const int m = rowm[row];
+                                if (m >= 0) {
+                                    const int nn = rowm[128 + row];
+                                    const float4 u = *reinterpret_cast<const float4*>(stg + row * STG_PITCH + col);
+                                    conv_epilogue_row4<ACT>(g, m, nn & 0x3FFFFFFF, (nn >> 30) != 0, o, u, bias4, one_n, os4, one_n, y2s4);
+                                }
+                            }
+                        };
+                        switch (g.act) {
+                            case MN_ACT_NONE: rows(ActTag<MN_ACT_NONE>{}); break;
+                            case MN_ACT_RELU: rows(ActTag<MN_ACT_RELU>{}); break;
+                            case MN_ACT_LRELU02: rows(ActTag<MN_ACT_LRELU02>{}); break;
+                            default: rows(ActTag<-1>{}); break;
                         }
                     }
                 }
@@ -293,7 +330,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         };
         // The epilogue of tile i runs after the first two halo tiles of tile i+1 have been split, so the feed/MMA warps have
         // ~2 x taps k-blocks of work queued while these warps drain TMEM and store tile i.
-        const int epi_after_cb = t.cbps > 1 ? 1 : 0;
+        const int epi_after_cb = t.epi_cb;
         int prev_work = -1;
         uint32_t hs = 0, hph = 0;
         constexpr bool gn = GN;       // fused GroupNorm(+swish) input transform: separate instantiation, zero cost when off
@@ -352,8 +389,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                 v = make_float4(tt[0], tt[1], tt[2], tt[3]);
                             }
                             v.x *= xs; v.y *= xs; v.z *= xs; v.w *= xs;
-                            amax = max(max(amax, __float_as_uint(v.x) & 0x7FFFFFFFu), max(__float_as_uint(v.y) & 0x7FFFFFFFu,
-                                       max(__float_as_uint(v.z) & 0x7FFFFFFFu, __float_as_uint(v.w) & 0x7FFFFFFFu)));
+                            amax = fmaxf(fmaxf(amax, fabsf(v.x)), fmaxf(fabsf(v.y), fmaxf(fabsf(v.z), fabsf(v.w))));   // 4 FMNMX (|.| is a free modifier)
                             const float h0 = __uint_as_float(__float_as_uint(v.x) & mask), h1 = __uint_as_float(__float_as_uint(v.y) & mask);
                             const float h2 = __uint_as_float(__float_as_uint(v.z) & mask), h3 = __uint_as_float(__float_as_uint(v.w) & mask);
                             const int c = box * 16 + j * 2;
@@ -375,13 +411,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // these generic writes precede the next TMA refill
                 mbar_arrive(bar(I_SD + hs));
-                hs ^= 1; if (hs == 0) hph ^= 1;
+                if (++hs == (uint32_t)HS) { hs = 0; hph ^= 1; }
                 if (cbi == epi_after_cb && prev_work >= 0) epilogue(prev_work);
             }
             prev_work = work;
         }
         if (prev_work >= 0) epilogue(prev_work);
-        conv_range_report(g, amax, t.prec == MN_PREC_F16X3_TC || t.prec == MN_PREC_F16X1_TC);
+        conv_range_report(g, __float_as_uint(amax), t.prec == MN_PREC_F16X3_TC || t.prec == MN_PREC_F16X1_TC);
     } else if (warp == 1) {
       if (CG == 1 || crank == 0) {
         // =========================== MMA issuer (whole warp converged, one elected lane issues) ===========================
@@ -392,7 +428,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const uint64_t desc_hi0 = make_b_desc(smem_base + off_b);           // stage 0, hi plane, k-step 0
         uint32_t as = 0, aph = 0, bs = 0, bph = 0, tcnt = 0;
         for (int work = cluster_id; work < total_work; work += num_clusters, ++tcnt) {
-            mbar_wait(bar(I_ACCE), (tcnt & 1) ^ 1);        // epilogue has drained the accumulators of the previous tile
+            const uint32_t acc_st = ACC_ST == 2 ? (tcnt & 1) : 0u, acc_ph = ACC_ST == 2 ? ((tcnt >> 1) & 1) : (tcnt & 1);
+            const uint32_t d_addr = tmem_base + acc_st * 2 * NT;
+            mbar_wait(bar(I_ACCE + acc_st), acc_ph ^ 1);   // epilogue has drained this accumulator stage
             tc_fence_after();
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait(bar(I_CD + as), aph);
@@ -405,16 +443,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                     for (int j = 0; j < KB / 16; ++j) {
                         if (CG == 2) {
-                            tc_mma_ts_cg2(tmem_base, a_hi + j * 8, dh0 + 2 * j, idesc, (kb | j) != 0);
+                            tc_mma_ts_cg2(d_addr, a_hi + j * 8, dh0 + 2 * j, idesc, (kb | j) != 0);
                             if (three) {
-                                tc_mma_ts_cg2(tmem_base + NT, a_hi + j * 8, dl0 + 2 * j, idesc, (kb | j) != 0);
-                                tc_mma_ts_cg2(tmem_base + NT, a_hi + 32 + j * 8, dh0 + 2 * j, idesc, 1);
+                                tc_mma_ts_cg2(d_addr + NT, a_hi + j * 8, dl0 + 2 * j, idesc, (kb | j) != 0);
+                                tc_mma_ts_cg2(d_addr + NT, a_hi + 32 + j * 8, dh0 + 2 * j, idesc, 1);
                             }
                         } else {
-                            tc_mma_ts(tmem_base, a_hi + j * 8, dh0 + 2 * j, idesc, (kb | j) != 0);
+                            tc_mma_ts(d_addr, a_hi + j * 8, dh0 + 2 * j, idesc, (kb | j) != 0);
                             if (three) {
-                                tc_mma_ts(tmem_base + NT, a_hi + j * 8, dl0 + 2 * j, idesc, (kb | j) != 0);
-                                tc_mma_ts(tmem_base + NT, a_hi + 32 + j * 8, dh0 + 2 * j, idesc, 1);
+                                tc_mma_ts(d_addr + NT, a_hi + j * 8, dl0 + 2 * j, idesc, (kb | j) != 0);
+                                tc_mma_ts(d_addr + NT, a_hi + 32 + j * 8, dh0 + 2 * j, idesc, 1);
                             }
                         }
                     }
@@ -431,7 +469,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (++as == A_STAGES) { as = 0; aph ^= 1; }
                 if (++bs == (uint32_t)BS) { bs = 0; bph ^= 1; }
             }
-            if (elect_one_sync()) { if (CG == 2) tc_commit_mc_cg2(bar(I_ACCF), cmask); else tc_commit(bar(I_ACCF)); }
+            if (elect_one_sync()) { if (CG == 2) tc_commit_mc_cg2(bar(I_ACCF + acc_st), cmask); else tc_commit(bar(I_ACCF + acc_st)); }
             __syncwarp();
         }
       }
@@ -482,7 +520,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     if (++as == A_STAGES) { as = 0; aph ^= 1; }
                 }
                 mbar_arrive(bar(I_HE + hs));         // all taps of this channel block have been read
-                hs ^= 1; if (hs == 0) hph ^= 1;
+                if (++hs == (uint32_t)HS) { hs = 0; hph ^= 1; }
             }
 
         }
@@ -573,12 +611,27 @@ Tc2Plan plan_tc2(const ConvGeom& g) {
     static int force_cg = -1;
     if (force_cg < 0) { const char* e = getenv("MN_TC_CG"); force_cg = e ? atoi(e) : 0; }
     t.cg = (t.cs == 2 && force_cg != 1) ? 2 : 1;
-    const int fixed = 2 * t.halo_stage_bytes + STG_BYTES + 1024 + 512 + 256 + 1024;
-    int bs = (SMEM_LIMIT - fixed) / (2 * (p.NT / t.cg) * 128);
+    // halo ring depth: a third stage when it still leaves >= 3 weight stages (cta_group::2 halves the weight stage) and the tile's
+    // K loop is short (<= 4 channel blocks): then the whole next tile's halos are in flight while this tile computes.
+    static int force_hs = -1, force_epi = -2;
+    if (force_hs < 0) { const char* e = getenv("MN_TC_HALO_STAGES"); force_hs = e ? atoi(e) : 0; }
+    if (force_epi < -1) { const char* e = getenv("MN_TC_EPI_CB"); force_epi = e ? atoi(e) : -1; }
+    const int b_stage_bytes = 2 * (p.NT / t.cg) * 128;
+    const int other = STG_BYTES + 1024 + 512 + 256 + 1024;
+    t.hstages = 2;
+    {
+        const bool fits3 = 3 * t.halo_stage_bytes + other + 3 * b_stage_bytes <= SMEM_LIMIT;
+        if (force_hs == 3 ? fits3 : (force_hs == 0 && fits3 && t.cbps <= 4 && t.cbps >= 2)) t.hstages = 3;
+    }
+    const int fixed = t.hstages * t.halo_stage_bytes + other;
+    int bs = (SMEM_LIMIT - fixed) / b_stage_bytes;
     if (bs > MAX_BSTAGES) bs = MAX_BSTAGES;
     if (bs < 2) return fail("not enough shared memory for 2 weight stages");
+    // epilogue of tile i after splitting channel block `epi_cb` of tile i+1 (its halos must fit the ring beside the running tile's)
+    t.epi_cb = t.cbps > 1 ? 1 : 0;
+    if (force_epi >= 0 && force_epi < t.cbps && force_epi < t.hstages) t.epi_cb = force_epi;
     t.bstages = bs;
-    p.smem = fixed + bs * 2 * (p.NT / t.cg) * 128;
+    p.smem = fixed + bs * b_stage_bytes;
     p.ok = true;
     return p;
 }
