@@ -241,11 +241,12 @@ def run_ours(args):
     lq_dev, locs_dev = lq_pin.to(dev), locs_pin.to(dev)
 
     lab_all = torch.cat(lab_dev, dim=0)
+    lab_cpu = torch.cat(labels, dim=0)        # the reference's caller keeps the labels on the CPU (test_sr.py:180 never moves them)
 
     def step(lq, locs):
         _, _, w = nets["encoder"](lq)
         # one generator call for the characters of all lines of the step (per-character style = its line's w), then per-line views
-        _, f64, f32_ = nets["tspgan"](styles=w.repeat_interleave(chars, dim=0), labels=lab_all, noise=None)
+        _, f64, f32_ = nets["tspgan"](styles=w.repeat_interleave(chars, dim=0), labels=lab_cpu, noise=None)
         p64 = [f64[b * chars:(b + 1) * chars] for b in range(lines)]
         p32 = [f32_[b * chars:(b + 1) * chars] for b in range(lines)]
         return nets["sr"](lq, p64, p32, locs)
@@ -377,7 +378,10 @@ def run_ours(args):
                        "lines_per_step_per_gpu": lines, "chars_per_line": chars, "parallelism": f"line-sharded dp{world}, no collective",
                        "precision": {0: "fp32 CUDA-core", 1: "fp16x3 tcgen05", 2: "bf16x3 tcgen05", 3: "fp16 tcgen05"}[ops.default_precision()],
                        "l2": "weights (352 MB fp32) + activations (>1 GB/line) exceed the 126 MB L2; no flush needed",
-                       "launch_mode": "cuda_graph_replay" if use_graph else "eager_module_calls", "eager_ms_per_step": ms_eager,
+                       "launch_mode": "cuda_graph_replay" if use_graph else "module_calls", "eager_ms_per_step": ms_eager,
+                       "module_api": "the three reference-facing module calls; each module replays a CUDA graph of its forward from "
+                                     "the second call with the same input signature on (MN_MODULE_GRAPHS=0: plain eager launches)"
+                                     if ops.MODULE_GRAPHS else "eager launches (MN_MODULE_GRAPHS=0)",
                        "cuda_graph": graph_info,
                        "gflop_per_step_per_gpu": gflop_per_line(chars) * lines,
                        "achieved_tflops_per_gpu": gflop_per_line(chars) * lines / ms_step},
@@ -443,13 +447,27 @@ def collective_record(nets, world, rank, dev, args):
             styles = synth.make_styles(n, 11).to(dev)
             own = n // W
 
+            per_call = min(chunk * W, n)
+            peer = None
+            if W > 1:       # in-kernel exchange: symmetric-memory receive buffers + per-character destination pointers (NVLink peer stores)
+                ok = torch.ones(1, device=dev)
+                try:
+                    peer = parallel.PeerPriorExchange(per_call, dev)
+                except Exception as exc:
+                    peer, ok = None, torch.zeros(1, device=dev)
+                    out["peer_stores_error"] = f"{type(exc).__name__}: {exc}"[:300]
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                if ok.item() < 0.5:
+                    peer = None
+
             def run_priors(mode):
                 # generated in `chunk`-character calls per rank; every chunk of W*chunk_local characters is its own block-cyclic round
-                per_call = min(chunk * W, n)
                 for c0 in range(0, n, per_call):
                     s_, l_ = styles[c0:c0 + per_call], labels[c0:c0 + per_call]
                     if mode == "all_gather":
                         parallel.generate_priors_sharded(gen, s_, l_)
+                    elif mode == "peer":
+                        peer.generate(gen, s_, l_)
                     else:
                         parallel.generate_priors_for_owners(gen, s_, l_, exchange=(mode == "all_to_all"))
 
@@ -467,6 +485,18 @@ def collective_record(nets, world, rank, dev, args):
                             "all_gather_bytes_received_per_rank": b["all_gather"],
                             "all_gather_gbps_per_rank": b["all_gather"] / max(ms_ag - ms_c, 1e-3) / 1e6,
                             "exchange": "NCCL all_to_all_single of fea64+fea32 (6 MiB/char) to line owners; all_gather = round-1 variant"})
+                if peer is not None:
+                    # correctness of the in-kernel exchange: the owned characters must equal the all-to-all result bit for bit
+                    a = parallel.generate_priors_for_owners(gen, styles[:per_call], labels[:per_call])
+                    b = peer.generate(gen, styles[:per_call], labels[:per_call])
+                    same = torch.tensor([1.0 if (torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])) else 0.0], device=dev)
+                    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+                    ms_peer = timed(lambda: run_priors("peer"))
+                    rec.update({"ms_with_peer_stores": ms_peer, "chars_per_sec_with_peer_stores": n / (ms_peer / 1e3),
+                                "peer_stores_equal_all_to_all": bool(same.item() > 0.5),
+                                "peer_stores": "the tap convolutions' epilogues store fea64/fea32 through per-character pointers into the "
+                                               "owners' symmetric-memory buffers (mn_conv_params.y2_ptrs, NVLink stores from the tcgen05 "
+                                               "kernel); one device-side barrier per round; no collective moves features"})
             out["priors1024"] = rec
             del labels, styles
         # ---------------- configs[3]: 64 lines x 16 chars end to end

@@ -115,6 +115,13 @@ typedef struct {
     float* x_absmax;
     int32_t* range_flag;
     int32_t range_tag;
+    /* Per-sample base pointers of the SECOND output: sample n's [OH][OW][y2_cs] block is written at y2_ptrs[n] instead of
+     * y2 + n*OH*OW*y2_cs (y2 must still be non-NULL to enable the output; it is not dereferenced).  The pointers may address the
+     * memory of PEER GPUs (NVLink-mapped symmetric memory): the epilogue's stores then deliver every character's prior features
+     * straight into the buffer of the rank that runs that character's SR decoder, tile by tile, while the MMAs of the next tile run
+     * -- the exchange of the character-sharded path (reference consumer: models/networks.py:442-445, 475-478) without a separate
+     * collective.  tcgen05 v2 kernel only, layers whose samples are whole pixel tiles (OH*OW >= 128), no split-K. */
+    float* const* y2_ptrs;
 } mn_conv_params;
 
 int mn_conv2d_nhwc(const mn_conv_params* p, void* stream);

@@ -15,6 +15,7 @@ struct ConvGeom {
     int M, K;
     int ktiles, ktiles_per_split, splits;
     float x_scale; float* x_absmax; int32_t* range_flag; int32_t range_tag;   // fp16-range management (tensor-core precisions)
+    float* const* y2_ptrs;     // per-sample base pointers of the second output (peer-GPU stores), tcgen05 v2 kernel only
 };
 
 // Range bookkeeping of the operand-split stage: `amax` = bits of the running fmaxf(|x * x_scale|) a thread has seen (fmaxf drops
@@ -113,7 +114,7 @@ __device__ __forceinline__ float mn_act_t(float v, int act) {
 }
 template <int ACT>
 __device__ __forceinline__ void conv_epilogue_row4(const ConvGeom& g, int m, int n, bool masked, int o, float4 v, const float4 bias4,
-                                                   bool have_os, const float4 os4, bool have_y2s, const float4 y2s4) {
+                                                   bool have_os, const float4 os4, bool have_y2s, const float4 y2s4, float* y2base) {
     if (g.out_scale) {
         const float4 s = have_os ? os4 : ldg4(g.out_scale + (size_t)n * g.os_stride + o);
         v.x *= s.x; v.y *= s.y; v.z *= s.z; v.w *= s.w;
@@ -133,7 +134,7 @@ __device__ __forceinline__ void conv_epilogue_row4(const ConvGeom& g, int m, int
             const float4 s = have_y2s ? y2s4 : ldg4(g.y2_scale + (size_t)n * g.y2s_stride + o);
             v.x *= s.x; v.y *= s.y; v.z *= s.z; v.w *= s.w;
         }
-        *reinterpret_cast<float4*>(g.y2 + (size_t)m * g.y2_cs + o) = v;
+        *reinterpret_cast<float4*>(y2base + (size_t)m * g.y2_cs + o) = v;     // y2base = g.y2, or the sample's (peer) block rebased to m
     }
 }
 

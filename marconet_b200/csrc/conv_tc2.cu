@@ -300,9 +300,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         // one sample per tile (every layer except the 4x4 .. 8x8 maps): its per-sample scale vectors are loaded once
                         const bool one_n = t.TN == 1;
                         float4 os4 = make_float4(1.f, 1.f, 1.f, 1.f), y2s4 = os4;
+                        float* y2base = g.y2;
                         if (one_n && n0 < g.N) {
                             if (g.out_scale) os4 = ldg4(g.out_scale + (size_t)n0 * g.os_stride + o);
                             if (g.y2 && g.y2_scale) y2s4 = ldg4(g.y2_scale + (size_t)n0 * g.y2s_stride + o);
+                            // per-sample (possibly peer-GPU) destination of the second output, rebased so that row index m addresses it
+                            if (g.y2_ptrs) y2base = g.y2_ptrs[n0] - (size_t)n0 * g.OH * g.OW * g.y2_cs;
                         }
                         auto rows = [&](auto tag) {
                             constexpr int ACT = decltype(tag)::value;
@@ -313,7 +316,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                 if (m >= 0) {
                                     const int nn = rowm[128 + row];
                                     const float4 u = *reinterpret_cast<const float4*>(stg + row * STG_PITCH + col);
-                                    conv_epilogue_row4<ACT>(g, m, nn & 0x3FFFFFFF, (nn >> 30) != 0, o, u, bias4, one_n, os4, one_n, y2s4);
+                                    conv_epilogue_row4<ACT>(g, m, nn & 0x3FFFFFFF, (nn >> 30) != 0, o, u, bias4, one_n, os4, one_n, y2s4, y2base);
                                 }
                             }
                         };
@@ -581,6 +584,7 @@ Tc2Plan plan_tc2(const ConvGeom& g) {
     while (t.TN > 1 && t.TN * t.HHt * t.HWd > 208) t.TN >>= 1;
     t.halo_rows = t.TN * t.HHt * t.HWd;
     if (t.halo_rows > 208) return fail("halo tile too large for shared memory");
+    if (g.y2_ptrs && t.TN != 1) return fail("per-sample output pointers need samples of at least one whole pixel tile (OH*OW >= 128)");
     if (t.HWd > 256 || t.HHt > 256 || t.TN > 256) return fail("TMA box dim");
     t.box_bytes = (t.halo_rows * 128 + 1023) & ~1023;
     t.halo_stage_bytes = 2 * t.box_bytes;
@@ -604,7 +608,7 @@ Tc2Plan plan_tc2(const ConvGeom& g) {
         const int items = t.m_groups * t.n_tiles, slots = mn_num_sms() / t.cs;
         while (t.ksplit * 2 * items <= slots && t.cblocks % (t.ksplit * 2) == 0 && t.cblocks / (t.ksplit * 2) >= 1 && t.ksplit < 8) t.ksplit *= 2;
         while (t.ksplit > 1 && (int64_t)t.ksplit * g.M * g.Cout * 4 > g.ws_bytes) t.ksplit >>= 1;
-        if (t.ksplit > 1 && (!g.ws || g.gn_mr || (g.Cout & 3))) t.ksplit = 1;
+        if (t.ksplit > 1 && (!g.ws || g.gn_mr || (g.Cout & 3) || g.y2_ptrs)) t.ksplit = 1;
     }
     t.cbps = t.cblocks / t.ksplit;
     // cta_group::2 pairs (see the kernel): default whenever the cluster has 2 CTAs; MN_TC_CG=1 forces the cta_group::1 + multicast path

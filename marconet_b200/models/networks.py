@@ -32,18 +32,101 @@ from .textvit_arch import TextViT
 SQRT2 = math.sqrt(2.0)
 
 
+class _CapturedCall:
+    """One module forward for one input signature, recorded into a CUDA graph: static inputs, a device error flag, static outputs."""
+    __slots__ = ("graph", "inputs", "outputs", "flag")
+
+
 class _PackedModule(nn.Module):
-    """Parameter container whose packed (kernel-layout) weights are rebuilt lazily."""
+    """Parameter container whose packed (kernel-layout) weights are rebuilt lazily.
+
+    Module-level CUDA graphs (round 2): the reference-facing ``forward()`` of each of the three modules is ~40-110 kernel launches
+    issued from Python; the eager path paid ~1 ms of host overhead per 16-character line (launch gaps plus a GPU pipeline drain at
+    every host round trip).  The SECOND call with the same input signature (shapes, device, precision plan) records the forward --
+    in the same no-host-round-trip mode GraphedLines uses -- and later calls replay it: inputs are copied into static buffers,
+    outputs are CLONED out of the graph's buffers (so results never alias a later call, as with the reference modules), and the
+    device-side error flag is read back where the eager path would have raised.  ``MN_MODULE_GRAPHS=0`` turns it off."""
+
+    _MG_LIMIT = 6           # captured signatures kept per module (least recently used is dropped)
 
     def __init__(self):
         super().__init__()
         self._packed = None
         self._packed_key = None
+        self._mg = None         # OrderedDict key -> _CapturedCall | "eager"
+        self._mg_hits = {}
         self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
 
     def _invalidate(self):
         self._packed = None
         self._packed_key = None
+        self._mg = None
+        self._mg_hits = {}
+
+    def _mg_run(self, key, sources, fn, fill=None):
+        """Replay (or, on the second sighting of ``key``, record) ``fn(*static_inputs) -> tuple of tensors``.  ``sources`` are the
+        caller's tensors (device or host) that are copied into the static inputs -- or, with ``fill``, (shape, dtype) specs of the
+        static inputs, which ``fill(static_inputs)`` then writes.  Returns the captured call (static outputs, flag) or None when
+        this call must run eagerly."""
+        if not ops.graphs_allowed():
+            return None
+        import collections
+        if self._mg is None:
+            self._mg = collections.OrderedDict()
+        key = (key, ops.graph_key())
+        ent = self._mg.get(key)
+        if ent is None:
+            if len(self._mg_hits) > 64:
+                self._mg_hits.clear()
+            n = self._mg_hits.get(key, 0) + 1
+            self._mg_hits[key] = n
+            if n < 2:
+                return None
+            ent = self._mg_capture(sources, fn, fill)
+            self._mg[key] = ent
+            self._mg_hits.pop(key, None)
+            while len(self._mg) > self._MG_LIMIT:
+                self._mg.popitem(last=False)
+        else:
+            self._mg.move_to_end(key)
+        if ent == "eager":
+            return None
+        if fill is not None:
+            fill(ent.inputs)
+        else:
+            for st, src in zip(ent.inputs, sources):
+                st.copy_(src, non_blocking=True)
+        ent.graph.replay()
+        return ent
+
+    def _mg_capture(self, sources, fn, fill):
+        dev = next(self.parameters()).device
+        try:
+            ent = _CapturedCall()
+            if fill is not None:
+                ent.inputs = [torch.empty(tuple(shape), dtype=dtype, device=dev) for shape, dtype in sources]
+                fill(ent.inputs)
+            else:
+                ent.inputs = [torch.empty(tuple(s.shape), dtype=s.dtype, device=dev) for s in sources]
+                for st, src in zip(ent.inputs, sources):
+                    st.copy_(src, non_blocking=True)
+            ent.flag = torch.zeros((1,), dtype=torch.int32, device=dev)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side), torch.no_grad(), ops.deferred_checks(ent.flag):
+                fn(*ent.inputs)                   # warm-up in the no-host-round-trip mode: fills its caches outside the capture
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            ent.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ent.graph, capture_error_mode="thread_local"), torch.no_grad(), ops.deferred_checks(ent.flag):
+                ent.flag.zero_()
+                ent.outputs = tuple(fn(*ent.inputs))
+            return ent
+        except Exception as exc:                  # capture is an optimisation: keep the eager path for this signature
+            import warnings
+            warnings.warn(f"marconet_b200: CUDA-graph capture of {type(self).__name__} failed ({type(exc).__name__}: {exc}); "
+                          f"this input signature keeps running eagerly")
+            return "eager"
 
     def _apply(self, fn, *a, **k):
         self._invalidate()
@@ -60,6 +143,7 @@ class _PackedModule(nn.Module):
             with torch.no_grad():
                 self._packed = self._pack(device)
             self._packed_key = key
+            self._mg, self._mg_hits = None, {}          # captured graphs hold the old packed weights
         return self._packed
 
     @staticmethod
@@ -95,9 +179,17 @@ class TextContextEncoderV2(_PackedModule):
         self._need_cuda(lq, "TextContextEncoderV2")
         with ops.on_device(lq):
             pk = self._get_packed(lq.device)
-            x = ops.nchw_to_nhwc(lq.float())
-            feat = self.resnet.run(pk["resnet"], x)
-            return self.transformer.run(pk["vit"], feat, branch=_branch)
+
+            def run(lq_):
+                x = ops.nchw_to_nhwc(lq_.float())
+                feat = self.resnet.run(pk["resnet"], x)
+                return self.transformer.run(pk["vit"], feat, branch=_branch)
+
+            if _branch is None and lq.dim() == 4:
+                ent = self._mg_run(("enc", tuple(lq.shape), lq.dtype, lq.device), [lq], run)
+                if ent is not None:
+                    return tuple(o.clone() for o in ent.outputs)
+            return run(lq)
 
 
 # =========================================================================================
@@ -245,14 +337,35 @@ class TextGenerator(_PackedModule):
 
     # ---- forward --------------------------------------------------------------------------
     @torch.no_grad()
-    def forward(self, styles, labels, noise=None, _branch=None):
+    def forward(self, styles, labels, noise=None, _branch=None, _tap_ptrs=None):
         """``_branch``: a second CUDA stream for the ToRGB chain (the 128-px prior image), which the feature taps -- and hence the
-        SR decoder -- do not depend on; the CALLER joins that stream before it reads the image."""
+        SR decoder -- do not depend on; the CALLER joins that stream before it reads the image.
+        ``_tap_ptrs`` = {64: ptrs, 32: ptrs} (int64 device tensors, one destination address per character): the two feature taps
+        are ADDITIONALLY stored through these per-character pointers by the epilogue of the convolution that produces them
+        (mn_conv_params.y2_ptrs) -- marconet_b200.parallel.PeerPriorExchange points them into the symmetric-memory buffers of
+        the ranks that own the characters' lines."""
         self._need_cuda(styles, "TSPGAN")
         with ops.on_device(styles):
+            if _tap_ptrs is not None:
+                return self._forward(styles, labels, _branch, _tap_ptrs)
+            if _branch is None and labels.dim() == 2 and styles.dim() == 2 and styles.shape[0] == labels.shape[0] and labels.numel() > 0:
+                self._get_packed(styles.device)
+                classes = self.input_text.TextEmbeddings.shape[0]
+                if not labels.is_cuda:      # the reference's caller keeps labels on the CPU (test_sr.py:180): host check, no round trip
+                    lab64 = labels.detach().to(torch.int64)
+                    if int(lab64.min()) < 0 or int(lab64.max()) >= classes:
+                        raise IndexError(f"character label out of range [0, {classes}) (reference: empty embedding slice, networks.py:211)")
+                else:
+                    lab64 = labels.detach().to(torch.int64)
+                ent = self._mg_run(("gen", tuple(styles.shape), tuple(labels.shape), styles.dtype, styles.device), [styles, lab64],
+                                   lambda st_, lab_: self._forward(st_, lab_, None))
+                if ent is not None:
+                    if labels.is_cuda:      # device-side range check: read the flag where the eager path would have raised
+                        ops.raise_deferred(int(ent.flag.item()))
+                    return tuple(o.clone() for o in ent.outputs)
             return self._forward(styles, labels, _branch)
 
-    def _forward(self, styles, labels, _branch):
+    def _forward(self, styles, labels, _branch, _tap_ptrs=None):
         dev = styles.device
         pk = self._get_packed(dev)
         if labels.dim() != 2:
@@ -285,11 +398,11 @@ class TextGenerator(_PackedModule):
         demod_all = ops.demod_batched(s_all, pk["demod_table"], pk["demod_total"])       # [N, sum Cout], one launch
         demods = [demod_all[:, e["demod_off"]:e["demod_off"] + e["cout"]] for e in st]
 
-        def styled(i, x, want_y, next_i=None):
+        def styled(i, x, want_y, next_i=None, tap_ptrs=None):
             e = st[i]
             y2s = None if next_i is None else s_of(st[next_i])
             return ops.conv2d(x, e["w"], 3, 3, pad=(1, 1), bias=e["bias"], out_scale=demods[i], act=ACT_LRELU02,
-                              gain=SQRT2, want_y=want_y, out2=(True if next_i is not None else None), y2_scale=y2s)
+                              gain=SQRT2, want_y=want_y, out2=(True if next_i is not None else None), y2_scale=y2s, out2_ptrs=tap_ptrs)
 
         main = torch.cuda.current_stream(dev) if _branch is not None else None
 
@@ -312,7 +425,8 @@ class TextGenerator(_PackedModule):
             ia, ib = 1 + 2 * j, 2 + 2 * j
             xu = ops.resample_modulate(y, s_of(st[ia]), up=True)     # bilinear x2 of the un-modulated map, then style
             xm = styled(ia, xu, False, next_i=ib)                    # only the pre-modulated operand of conv b is kept
-            y = styled(ib, xm, True)
+            tp = None if (_tap_ptrs is None or l != 1) else _tap_ptrs.get(xm.shape[2])     # the tap layers (64 / 32 columns wide)
+            y = styled(ib, xm, True, tap_ptrs=tp)
             skip = rgb(y, pk["rgb"][1 + j], skip)
             taps[y.shape[2]] = y                                     # the reference picks its taps by WIDTH (networks.py:153-158)
         if 64 not in taps or 32 not in taps:
@@ -326,8 +440,8 @@ class TSPGAN(nn.Module):
         super().__init__()
         self.TextGenerator = TextGenerator(size=out_size, style_dim=num_style_feat, n_mlp=num_mlp, class_num=class_num)
 
-    def forward(self, styles, labels, noise, _branch=None):
-        return self.TextGenerator(styles, labels, noise, _branch=_branch)
+    def forward(self, styles, labels, noise, _branch=None, _tap_ptrs=None):
+        return self.TextGenerator(styles, labels, noise, _branch=_branch, _tap_ptrs=_tap_ptrs)
 
 
 # =========================================================================================
@@ -591,7 +705,49 @@ class TSPSRNet(_PackedModule):
     def forward(self, lq, priors64, priors32, locs, _trunk=None):
         self._need_cuda(lq, "TSPSRNet")
         with ops.on_device(lq):
+            ent = self._forward_graphed(lq, priors64, priors32, locs) if _trunk is None else None
+            if ent is not None:
+                ops.raise_deferred(int(ent.flag.item()))      # the eager path raises on an empty window before launching; here after
+                return ent.outputs[0].clone()
             return self._forward(lq, priors64, priors32, locs, _trunk)
+
+    def _forward_graphed(self, lq, priors64, priors32, locs):
+        """Module-level CUDA graph of the decoder for this (lines, characters-per-line) signature; None -> run eagerly."""
+        if not ops.graphs_allowed() or lq.dim() != 4 or len(priors64) != len(priors32) or not isinstance(locs, torch.Tensor) or locs.dim() != 2:
+            return None
+        bsz = lq.shape[0]
+        counts = [int(p.shape[0]) for p in priors32] + [0] * (bsz - len(priors32))
+        nc = sum(counts)
+        d = self.dim
+        if (nc == 0 or len(priors64) != bsz or min(counts) == 0 or [int(p.shape[0]) for p in priors64] != counts
+                or locs.shape[0] < bsz or locs.shape[1] < 2 * max(counts)):
+            return None
+        for p, ch, sz in [(p, d, 64) for p in priors64] + [(p, 512, 32) for p in priors32]:
+            if p.dim() != 4 or tuple(p.shape[1:]) != (ch, sz, sz) or not p.is_cuda:
+                return None
+        self._get_packed(lq.device)
+        # static inputs: the LR lines, the boxes, and all priors of all lines as two NHWC tensors (each line's priors are copied
+        # straight into their slice: one contiguous device copy per line when the caller passes the generator's own outputs)
+        specs = [(lq.shape, torch.float32), (locs.shape, torch.float32), ((nc, 64, 64, d), torch.float32), ((nc, 32, 32, 512), torch.float32)]
+
+        def fill(st):
+            st[0].copy_(lq, non_blocking=True)
+            st[1].copy_(locs.detach(), non_blocking=True)
+            o = 0
+            for i, n in enumerate(counts[:len(priors64)]):
+                if n:
+                    st[2][o:o + n].copy_(priors64[i].permute(0, 2, 3, 1), non_blocking=True)
+                    st[3][o:o + n].copy_(priors32[i].permute(0, 2, 3, 1), non_blocking=True)
+                o += n
+
+        def run(lq_, locs_, p64_, p32_):
+            l64, l32, o = [], [], 0
+            for n in counts:
+                l64.append(p64_[o:o + n].permute(0, 3, 1, 2)); l32.append(p32_[o:o + n].permute(0, 3, 1, 2)); o += n
+            return (self._forward(lq_, l64[:len(priors64)], l32[:len(priors32)], locs_, None),)
+
+        key = ("sr", tuple(lq.shape), tuple(counts), len(priors64), tuple(locs.shape), lq.device)
+        return self._mg_run(key, specs, run, fill)
 
     def _forward(self, lq, priors64, priors32, locs, _trunk):
         dev = lq.device

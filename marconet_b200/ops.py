@@ -30,8 +30,25 @@ def set_default_precision(p):
     _DEFAULT_PRECISION = int(p)
 
 
+def graph_key():
+    """Everything process-global that a captured CUDA graph of this library bakes in."""
+    return (_DEFAULT_PRECISION, PLAN_VERSION, MAX_CTAS, FUSE_GN)
+
+
+def graphs_allowed():
+    """Module-level graph replay is off inside another capture, inside ops.deferred_checks (GraphedLines owns the step then) and
+    while a calibration records per-layer statistics."""
+    return (MODULE_GRAPHS and getattr(_TLS, "deferred_flag", None) is None and getattr(_TLS, "calib", None) is None
+            and not torch.cuda.is_current_stream_capturing())
+
+
+MODULE_GRAPHS = _os.environ.get("MN_MODULE_GRAPHS", "1") != "0"
+
+
 def set_max_ctas(n):
     """Cap the persistent conv kernels at n CTAs (0 = all SMs); returns the previous cap."""
+    global MAX_CTAS
+    MAX_CTAS = int(n)
     return _lib.load().mn_set_max_ctas(int(n))
 
 
@@ -111,6 +128,8 @@ class use_workspace:
 
 
 PLAN = {}     # layer name -> (precision or None, x_scale): the per-layer precision plan of this process (pipeline.tune_precision)
+PLAN_VERSION = 0   # bumped whenever a layer's plan changes: captured CUDA graphs bake the plan in and key on it
+MAX_CTAS = 0       # mirror of mn_set_max_ctas (grid sizes are baked into captured graphs)
 
 
 class ConvWeight:
@@ -146,6 +165,8 @@ class ConvWeight:
         if x_scale is not None:
             self.x_scale = float(x_scale)
         PLAN[self.name] = (self.precision, self.x_scale)
+        global PLAN_VERSION
+        PLAN_VERSION += 1
 
     @classmethod
     def from_tag(cls, tag):
@@ -313,7 +334,7 @@ TC_MIN_FLOP = 3.0e7    # tiny launches are latency-bound either way and stay on 
 
 def conv2d(x, w, kh, kw, stride=(1, 1), pad=(0, 0), bias=None, out_scale=None, residual=None,
            res_broadcast=False, act=ACT_NONE, gain=1.0, out=None, out2=None, y2_scale=None,
-           valid_w=None, precision=None, want_y=True, split_k=0, gn=None, gn_fuse=None):
+           valid_w=None, precision=None, want_y=True, split_k=0, gn=None, gn_fuse=None, out2_ptrs=None):
     """mn_conv2d_nhwc.  ``w`` is the packed [KH*KW*Cin, Cout] matrix.  Returns y (or (y, y2)).
     ``gn=(mean_rstd, gamma, beta)``: the conv input is swish(GroupNorm(x)); fused into the tcgen05 v2 kernel's operand-split
     stage when ``gn_fuse`` is true and that kernel runs the layer, otherwise applied by mn_groupnorm_apply first.
@@ -341,6 +362,14 @@ def conv2d(x, w, kh, kw, stride=(1, 1), pad=(0, 0), bias=None, out_scale=None, r
             raise RuntimeError(f"conv2d: out has shape {tuple(y.shape)}, expected {(n, oh, ow, cout)}")
         p.y = y.data_ptr(); p.y_cs = y_cs
     y2 = None
+    if out2_ptrs is not None:
+        # second output scattered through per-sample base pointers (int64 device tensor [N], possibly PEER-GPU addresses):
+        # mn_conv_params.y2_ptrs; dense [OH, OW, Cout] blocks.  Nothing local is allocated for it.
+        if out2 is not None or out2_ptrs.dtype != torch.int64 or not out2_ptrs.is_cuda or out2_ptrs.numel() != n or not out2_ptrs.is_contiguous():
+            raise RuntimeError("conv2d: out2_ptrs must be a contiguous int64 CUDA tensor with one pointer per sample (and out2 unset)")
+        p.y2 = out2_ptrs.data_ptr(); p.y2_cs = cout; p.y2_ptrs = out2_ptrs.data_ptr()
+        if y2_scale is not None:
+            p.y2_scale = y2_scale.data_ptr(); p.y2_scale_stride = y2_scale.stride(0)
     if out2 is not None:
         y2 = out2 if isinstance(out2, torch.Tensor) else torch.empty((n, oh, ow, cout), dtype=torch.float32, device=x.device)
         _, _, _, _, y2_cs = nhwc_info(y2, "out2")

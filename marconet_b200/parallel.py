@@ -147,3 +147,67 @@ def exchange_bytes_per_rank(n_chars, world, bytes_per_char=6 * (1 << 20)):
     """Bytes each rank sends (= receives) in generate_priors_for_owners vs in the all-gather variant."""
     owned = n_chars // world
     return dict(all_to_all=owned * bytes_per_char * (world - 1) // world, all_gather=(n_chars - owned) * bytes_per_char)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# In-kernel exchange (round 2): the convolution that produces a feature tap stores it -- from its own epilogue, tile by tile,
+# while the MMAs of the next tile run -- straight into the symmetric-memory receive buffer of the rank that owns the character's
+# line (mn_conv_params.y2_ptrs; NVLink peer stores).  No separate collective moves prior features any more; one device-side
+# barrier per round publishes them.  Same block-cyclic plan as generate_priors_for_owners.
+# ---------------------------------------------------------------------------------------------------------------------
+class PeerPriorExchange:
+    """Receive buffers in symmetric memory (torch.distributed._symmetric_memory: cuMem allocations mapped into every rank of
+    the box) + the per-character destination pointer tables of one block-cyclic round of ``n_chars`` characters.
+
+    >>> ex = PeerPriorExchange(n_chars=1024, device=dev)            # collective: every rank constructs it
+    >>> f64, f32 = ex.generate(tspgan, styles_all, labels_all)      # this rank's OWNED characters, natural order
+
+    ``slots`` receive buffers are used round-robin so that the SR decoder may still read round k while round k+1 is written."""
+
+    F64 = 64 * 64 * 256
+    F32 = 32 * 32 * 512
+
+    def __init__(self, n_chars, device, group=None, slots=2):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.n, self.sub = n_chars, owner_blocks(n_chars, self.world)
+        self.own = n_chars // self.world
+        self.slots, self.slot = slots, 0
+        self.device = torch.device(device)
+        per_slot = self.own * (self.F64 + self.F32)
+        self.buf = symm_mem.empty(slots * per_slot, dtype=torch.float32, device=self.device)
+        self.handle = symm_mem.rendezvous(self.buf, self.group)
+        peers = [int(p) for p in self.handle.buffer_ptrs]
+        w, r, sub = self.world, self.rank, self.sub
+        self.ptrs = []
+        for s in range(slots):
+            t64, t32 = [], []
+            for d in range(w):                                   # local sample j = d*sub + i goes to owner d, position r*sub + i
+                base64 = peers[d] + 4 * s * per_slot
+                base32 = base64 + 4 * self.own * self.F64
+                for i in range(sub):
+                    t64.append(base64 + 4 * (r * sub + i) * self.F64)
+                    t32.append(base32 + 4 * (r * sub + i) * self.F32)
+            self.ptrs.append({64: torch.tensor(t64, dtype=torch.int64).to(self.device), 32: torch.tensor(t32, dtype=torch.int64).to(self.device)})
+        self.idx = torch.cat([torch.arange(o * w * sub + r * sub, o * w * sub + (r + 1) * sub) for o in range(w)])
+        self.idx_dev = self.idx.to(self.device)
+        self.per_slot = per_slot
+
+    def local_views(self, slot):
+        """(fea64 [own,256,64,64], fea32 [own,512,32,32]) NCHW-shaped channels_last views of this rank's receive buffer."""
+        base = slot * self.per_slot
+        f64 = self.buf[base:base + self.own * self.F64].view(self.own, 64, 64, 256).permute(0, 3, 1, 2)
+        f32 = self.buf[base + self.own * self.F64:base + self.per_slot].view(self.own, 32, 32, 512).permute(0, 3, 1, 2)
+        return f64, f32
+
+    def generate(self, generator, styles, labels):
+        """``styles`` / ``labels``: ALL n characters (identical on every rank).  Every rank generates its block-cyclic share; the tap
+        convolutions deliver the features to the owners; returns the OWNED characters' (fea64, fea32), valid until ``slots``
+        further rounds have been generated."""
+        slot = self.slot
+        self.slot = (self.slot + 1) % self.slots
+        lab = labels.index_select(0, self.idx_dev if labels.is_cuda else self.idx)
+        generator(styles.index_select(0, self.idx_dev), lab, None, _tap_ptrs=self.ptrs[slot])
+        self.handle.barrier(channel=slot)                        # device-side, stream-ordered: every rank's stores have landed
+        return self.local_views(slot)

@@ -170,6 +170,7 @@ def tune_precision(encoder, tspgan, sr, lq, labels=None, locs=None, target_absma
             cw.set_plan(x_scale=1.0)
             cw.precision = None
             ops.PLAN[cw.name] = (None, 1.0)
+        ops.PLAN_VERSION += 1
         try:
             ops.set_default_precision(ops.PREC_BF16X3_TC)
             with ops.calibration(dev) as cal:
@@ -223,4 +224,5 @@ def load_precision_plan(path_or_dict, *modules):
     for cw in conv_layers(*modules):
         if cw.name in ops.PLAN:
             cw.precision, cw.x_scale = ops.PLAN[cw.name]
+    ops.PLAN_VERSION += 1
     return plan

@@ -1,0 +1,54 @@
+"""In-kernel exchange of the character-sharded generator (marconet_b200.parallel.PeerPriorExchange): the tap convolutions store
+fea64 / fea32 through per-character pointers into the owners' symmetric-memory buffers (NVLink peer stores from the tcgen05
+kernel's epilogue).  Needs 2 GPUs in one box; one process per GPU over NCCL, like the product path."""
+import os
+import socket
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, ok):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from marconet_b200 import parallel
+        from marconet_b200.models import networks
+        from marconet_b200.testing import synth
+        gen = networks.TSPGAN()
+        gen.load_state_dict(synth.make_checkpoints(0)["tspgan"], strict=True)
+        gen = gen.eval().to(dev)
+        n = 8
+        styles, labels = synth.make_styles(n, 4).to(dev), synth.make_labels(n, 4).to(dev)
+        with torch.no_grad():
+            ref64, ref32 = parallel.generate_priors_for_owners(gen, styles, labels)       # NCCL all-to-all path
+            full = gen(styles, labels, None)                                             # every character, locally
+            ex = parallel.PeerPriorExchange(n, dev)
+            good = True
+            for rep in range(3):                                                          # slots are reused round-robin
+                f64, f32 = ex.generate(gen, styles, labels)
+                torch.cuda.synchronize()
+                good &= torch.equal(f64, ref64) and torch.equal(f32, ref32)
+            own = slice(rank * n // world, (rank + 1) * n // world)
+            good &= torch.equal(ref64, full[1][own]) and torch.equal(ref32, full[2][own])
+            good &= f64.permute(0, 2, 3, 1).is_contiguous()
+        ok[rank] = 1 if good else 0
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_store_exchange_equals_all_to_all_world2():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ok = mp.get_context("spawn").Array("i", [0, 0])
+    mp.spawn(_worker, args=(2, port, ok), nprocs=2, join=True)
+    assert list(ok) == [1, 1]
