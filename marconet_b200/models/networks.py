@@ -99,6 +99,14 @@ class _PackedModule(nn.Module):
         ent.graph.replay()
         return ent
 
+    def _mg_side(self, device):
+        """(second stream, split-K scratch) for the parallel branch of a recorded forward; one per module."""
+        side = getattr(self, "_mg_side_res", None)
+        if side is None or side[1].device != device:
+            side = (torch.cuda.Stream(device=device), torch.empty(ops._WS_BYTES // 4, dtype=torch.float32, device=device))
+            self._mg_side_res = side
+        return side
+
     def _mg_capture(self, sources, fn, fill):
         dev = next(self.parameters()).device
         try:
@@ -180,13 +188,21 @@ class TextContextEncoderV2(_PackedModule):
         with ops.on_device(lq):
             pk = self._get_packed(lq.device)
 
-            def run(lq_):
+            def run(lq_, branch=_branch):
                 x = ops.nchw_to_nhwc(lq_.float())
                 feat = self.resnet.run(pk["resnet"], x)
-                return self.transformer.run(pk["vit"], feat, branch=_branch)
+                return self.transformer.run(pk["vit"], feat, branch=branch)
+
+            def run_two_streams(lq_):
+                # inside the recorded graph the classification / box branches run beside the style branch on a second stream
+                # (own split-K scratch) and are joined before the graph ends
+                br = self._mg_side(lq_.device)
+                out = run(lq_, br)
+                torch.cuda.current_stream(lq_.device).wait_stream(br[0])
+                return out
 
             if _branch is None and lq.dim() == 4:
-                ent = self._mg_run(("enc", tuple(lq.shape), lq.dtype, lq.device), [lq], run)
+                ent = self._mg_run(("enc", tuple(lq.shape), lq.dtype, lq.device), [lq], run_two_streams)
                 if ent is not None:
                     return tuple(o.clone() for o in ent.outputs)
             return run(lq)
@@ -357,8 +373,15 @@ class TextGenerator(_PackedModule):
                         raise IndexError(f"character label out of range [0, {classes}) (reference: empty embedding slice, networks.py:211)")
                 else:
                     lab64 = labels.detach().to(torch.int64)
+                def run_two_streams(st_, lab_):
+                    # inside the recorded graph the ToRGB chain (the prior image) runs on a second stream beside the main convs
+                    br = self._mg_side(st_.device)[0]
+                    out = self._forward(st_, lab_, br)
+                    torch.cuda.current_stream(st_.device).wait_stream(br)
+                    return out
+
                 ent = self._mg_run(("gen", tuple(styles.shape), tuple(labels.shape), styles.dtype, styles.device), [styles, lab64],
-                                   lambda st_, lab_: self._forward(st_, lab_, None))
+                                   run_two_streams)
                 if ent is not None:
                     if labels.is_cuda:      # device-side range check: read the flag where the eager path would have raised
                         ops.raise_deferred(int(ent.flag.item()))

@@ -35,7 +35,8 @@ def _worker(rank, world, port, ok):
                 torch.cuda.synchronize()
                 good &= torch.equal(f64, ref64) and torch.equal(f32, ref32)
             own = slice(rank * n // world, (rank + 1) * n // world)
-            good &= torch.equal(ref64, full[1][own]) and torch.equal(ref32, full[2][own])
+            # against an UNSHARDED call only to tolerance: the kernel picks tiles / split-K by batch size (8 vs 4 characters)
+            good &= bool((ref64 - full[1][own]).abs().max() < 1e-3) and bool((ref32 - full[2][own]).abs().max() < 1e-3)
             good &= f64.permute(0, 2, 3, 1).is_contiguous()
         ok[rank] = 1 if good else 0
     finally:
