@@ -437,6 +437,7 @@ def collective_record(nets, world, rank, dev, args):
         return float(ms.item())
 
     out = {}
+    peer = None
     gen, enc, sr = nets["tspgan"], nets["encoder"], nets["sr"]
     chunk = 128                                     # characters per TSPGAN call (bounds activation memory at N=1)
     with torch.no_grad():
@@ -448,7 +449,6 @@ def collective_record(nets, world, rank, dev, args):
             own = n // W
 
             per_call = min(chunk * W, n)
-            peer = None
             if W > 1:       # in-kernel exchange: symmetric-memory receive buffers + per-character destination pointers (NVLink peer stores)
                 ok = torch.ones(1, device=dev)
                 try:
@@ -527,7 +527,7 @@ def collective_record(nets, world, rank, dev, args):
             own_lines = max(1, lines_round // W)            # ... of which this rank owns the rank-th block
             lq_all_dev = lq_all.to(dev)
 
-            def char_sharded():
+            def char_sharded(use_peer=False):
                 _, _, w = enc(lq_own)
                 if W > 1:
                     w_all = torch.empty((L, w.shape[1]), dtype=w.dtype, device=dev)
@@ -538,7 +538,10 @@ def collective_record(nets, world, rank, dev, args):
                 res = []
                 for k in range(rounds):
                     c0 = k * per_call
-                    f64, f32_ = parallel.generate_priors_for_owners(gen, styles[c0:c0 + per_call], lab_all[c0:c0 + per_call])
+                    if use_peer:
+                        f64, f32_ = peer.generate(gen, styles[c0:c0 + per_call], lab_all[c0:c0 + per_call])
+                    else:
+                        f64, f32_ = parallel.generate_priors_for_owners(gen, styles[c0:c0 + per_call], lab_all[c0:c0 + per_call])
                     g0 = k * lines_round + rank * own_lines                 # first global line of this rank's block in round k
                     p64 = [f64[b * C:(b + 1) * C] for b in range(own_lines)]
                     p32 = [f32_[b * C:(b + 1) * C] for b in range(own_lines)]
@@ -554,6 +557,9 @@ def collective_record(nets, world, rank, dev, args):
                 rec.update({"ms_char_sharded_with_all_to_all": ms_char, "chars_per_sec_char_sharded": L * C / (ms_char / 1e3),
                             "all_to_all_bytes_sent_per_rank": b["all_to_all"], "rounds": rounds,
                             "exchange": "all_gather of w (2 KB/line) + NCCL all_to_all_single of fea64/fea32 to line owners"})
+                if peer is not None and peer.n == per_call:
+                    ms_peer = timed(lambda: char_sharded(True))
+                    rec.update({"ms_char_sharded_with_peer_stores": ms_peer, "chars_per_sec_char_sharded_peer_stores": L * C / (ms_peer / 1e3)})
             out["lines64"] = rec
     return out if rank == 0 else None
 

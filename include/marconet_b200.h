@@ -122,6 +122,11 @@ typedef struct {
      * -- the exchange of the character-sharded path (reference consumer: models/networks.py:442-445, 475-478) without a separate
      * collective.  tcgen05 v2 kernel only, layers whose samples are whole pixel tiles (OH*OW >= 128), no split-K. */
     float* const* y2_ptrs;
+    /* GroupNorm statistics of the OUTPUT accumulated by the epilogue (models/networks.py:508-512: the tensor this convolution writes
+     * is normalised next): per (sample, group of 32 output channels) sum and sum of squares of y, fp32 partials per warp and tile
+     * added into [N][Cout/32][2] doubles with atomics (the caller zeroes the buffer; columns beyond valid_w contribute 0).
+     * tcgen05 v2 kernel, whole-tile samples (OH*OW >= 128), no split-K; finish with mn_groupnorm_finalize. */
+    double* gn_stats_out;
 } mn_conv_params;
 
 int mn_conv2d_nhwc(const mn_conv_params* p, void* stream);
@@ -198,6 +203,10 @@ int mn_groupnorm_swish(const float* x, int x_cs, float* y, int y_cs, const float
  * statistics -> mean_rstd [N][C/cpg][2] fp32 (stats_ws: >= 2*N*(C/cpg) doubles), and the elementwise apply. */
 int mn_groupnorm_stats(const float* x, int x_cs, int N, int H, int W, int C, int cpg, float eps,
                        const int32_t* valid_w, double* stats_ws, float* mean_rstd, void* stream);
+/* Second half of mn_groupnorm_stats alone: sums [N][C/cpg][2] (sum, sum of squares; fp64) -> mean_rstd.  Used when the PRODUCING
+ * convolution accumulated the sums in its epilogue (mn_conv_params.gn_stats_out): no separate read pass over the tensor. */
+int mn_groupnorm_finalize(const double* stats_ws, int N, int H, int W, int C, int cpg, float eps, const int32_t* valid_w,
+                          float* mean_rstd, void* stream);
 int mn_groupnorm_apply(const float* x, int x_cs, float* y, int y_cs, const float* gamma, const float* beta,
                        const float* mean_rstd, int N, int H, int W, int C, int cpg, int swish,
                        const int32_t* valid_w, void* stream);

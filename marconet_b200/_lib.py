@@ -34,7 +34,7 @@ class ConvParams(Structure):
         ("w_tc_hi", c_void_p), ("w_tc_lo", c_void_p), ("w_tc_scale", c_void_p),
         ("gn_mean_rstd", c_void_p), ("gn_gamma", c_void_p), ("gn_beta", c_void_p), ("gn_swish", c_int),
         ("x_scale", c_float), ("x_absmax", c_void_p), ("range_flag", c_void_p), ("range_tag", c_int32),
-        ("y2_ptrs", c_void_p),
+        ("y2_ptrs", c_void_p), ("gn_stats_out", c_void_p),
     ]
 
 
@@ -57,6 +57,7 @@ SYMBOLS = {
     "mn_conv2d_tc_supported": (c_int, [POINTER(ConvParams)]),
     "mn_conv2d_tc_version": (c_int, [POINTER(ConvParams)]),
     "mn_groupnorm_stats": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mn_groupnorm_finalize": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
     "mn_groupnorm_apply": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                    c_void_p, c_void_p]),
     "mn_conv_pack_weights_tc": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

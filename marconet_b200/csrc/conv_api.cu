@@ -38,7 +38,8 @@ static int make_geom(const mn_conv_params* p, ConvGeom& g) {
     g.M = (int)M; g.K = p->KH * p->KW * p->Cin;
     g.ktiles = g.ktiles_per_split = 0; g.splits = 1;
     g.x_scale = p->x_scale > 0.f ? p->x_scale : 1.f; g.x_absmax = p->x_absmax; g.range_flag = p->range_flag; g.range_tag = p->range_tag;
-    g.y2_ptrs = p->y2_ptrs;
+    g.y2_ptrs = p->y2_ptrs; g.gn_stats_out = p->gn_stats_out;
+    MN_REQUIRE(!p->gn_stats_out || (p->Cout % 32 == 0 && p->y), "mn_conv2d_nhwc: gn_stats_out needs Cout % 32 == 0 and the y output");
     MN_REQUIRE(!p->y2_ptrs || p->y2, "mn_conv2d_nhwc: y2_ptrs needs the second output enabled (y2 != NULL)");
     return MN_OK;
 }
@@ -56,8 +57,8 @@ extern "C" int mn_conv2d_nhwc(const mn_conv_params* p, void* stream) {
     if (rc != MN_OK) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool v2 = p->precision != MN_PREC_FP32_SIMT && !tc_force_v1() && mn_conv_tc2_supported(g, nullptr);
-    if (g.y2_ptrs && !v2) {
-        mn_set_error("mn_conv2d_nhwc: per-sample output pointers (y2_ptrs) exist only in the tcgen05 v2 kernel");
+    if ((g.y2_ptrs || g.gn_stats_out) && !v2) {
+        mn_set_error("mn_conv2d_nhwc: per-sample output pointers (y2_ptrs) / epilogue GroupNorm statistics (gn_stats_out) exist only in the tcgen05 v2 kernel");
         return MN_ERR_UNSUPPORTED;
     }
     if (g.gn_mr && !v2) {

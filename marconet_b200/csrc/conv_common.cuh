@@ -16,6 +16,7 @@ struct ConvGeom {
     int ktiles, ktiles_per_split, splits;
     float x_scale; float* x_absmax; int32_t* range_flag; int32_t range_tag;   // fp16-range management (tensor-core precisions)
     float* const* y2_ptrs;     // per-sample base pointers of the second output (peer-GPU stores), tcgen05 v2 kernel only
+    double* gn_stats_out;      // [N][Cout/32][2] sum / sum of squares of the output (GroupNorm statistics in the epilogue), v2 only
 };
 
 // Range bookkeeping of the operand-split stage: `amax` = bits of the running fmaxf(|x * x_scale|) a thread has seen (fmaxf drops
@@ -113,8 +114,8 @@ __device__ __forceinline__ float mn_act_t(float v, int act) {
     return mn_apply_act(v, act);
 }
 template <int ACT>
-__device__ __forceinline__ void conv_epilogue_row4(const ConvGeom& g, int m, int n, bool masked, int o, float4 v, const float4 bias4,
-                                                   bool have_os, const float4 os4, bool have_y2s, const float4 y2s4, float* y2base) {
+__device__ __forceinline__ float4 conv_epilogue_row4(const ConvGeom& g, int m, int n, bool masked, int o, float4 v, const float4 bias4,
+                                                     bool have_os, const float4 os4, bool have_y2s, const float4 y2s4, float* y2base) {
     if (g.out_scale) {
         const float4 s = have_os ? os4 : ldg4(g.out_scale + (size_t)n * g.os_stride + o);
         v.x *= s.x; v.y *= s.y; v.z *= s.z; v.w *= s.w;
@@ -130,12 +131,14 @@ __device__ __forceinline__ void conv_epilogue_row4(const ConvGeom& g, int m, int
     if (masked) v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (g.y) *reinterpret_cast<float4*>(g.y + (size_t)m * g.y_cs + o) = v;
     if (g.y2) {
+        float4 u = v;
         if (g.y2_scale) {
             const float4 s = have_y2s ? y2s4 : ldg4(g.y2_scale + (size_t)n * g.y2s_stride + o);
-            v.x *= s.x; v.y *= s.y; v.z *= s.z; v.w *= s.w;
+            u.x *= s.x; u.y *= s.y; u.z *= s.z; u.w *= s.w;
         }
-        *reinterpret_cast<float4*>(y2base + (size_t)m * g.y2_cs + o) = v;     // y2base = g.y2, or the sample's (peer) block rebased to m
+        *reinterpret_cast<float4*>(y2base + (size_t)m * g.y2_cs + o) = u;     // y2base = g.y2, or the sample's (peer) block rebased to m
     }
+    return v;      // the stored y values (GroupNorm statistics in the epilogue)
 }
 
 int mn_conv_simt_plan_splits(const ConvGeom& g, int64_t ws_bytes, int requested);

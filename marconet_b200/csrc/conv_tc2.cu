@@ -307,6 +307,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             // per-sample (possibly peer-GPU) destination of the second output, rebased so that row index m addresses it
                             if (g.y2_ptrs) y2base = g.y2_ptrs[n0] - (size_t)n0 * g.OH * g.OW * g.y2_cs;
                         }
+                        float gs = 0.f, gq = 0.f;       // GroupNorm statistics of this thread's 16 rows x 4 channels (one group)
                         auto rows = [&](auto tag) {
                             constexpr int ACT = decltype(tag)::value;
 #pragma unroll 4
@@ -316,7 +317,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                 if (m >= 0) {
                                     const int nn = rowm[128 + row];
                                     const float4 u = *reinterpret_cast<const float4*>(stg + row * STG_PITCH + col);
-                                    conv_epilogue_row4<ACT>(g, m, nn & 0x3FFFFFFF, (nn >> 30) != 0, o, u, bias4, one_n, os4, one_n, y2s4, y2base);
+                                    const float4 w4 = conv_epilogue_row4<ACT>(g, m, nn & 0x3FFFFFFF, (nn >> 30) != 0, o, u, bias4, one_n, os4, one_n, y2s4, y2base);
+                                    if (g.gn_stats_out) {
+                                        gs += (w4.x + w4.y) + (w4.z + w4.w);
+                                        gq = fmaf(w4.x, w4.x, fmaf(w4.y, w4.y, fmaf(w4.z, w4.z, fmaf(w4.w, w4.w, gq))));
+                                    }
                                 }
                             }
                         };
@@ -325,6 +330,17 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             case MN_ACT_RELU: rows(ActTag<MN_ACT_RELU>{}); break;
                             case MN_ACT_LRELU02: rows(ActTag<MN_ACT_LRELU02>{}); break;
                             default: rows(ActTag<-1>{}); break;
+                        }
+                        if (g.gn_stats_out) {
+                            // lanes 0-7 / 8-15 (and 16-23 / 24-31, the odd rows) hold the two 32-channel groups of this 64-column half
+#pragma unroll
+                            for (int sh = 1; sh <= 4; sh <<= 1) { gs += __shfl_xor_sync(0xffffffffu, gs, sh); gq += __shfl_xor_sync(0xffffffffu, gq, sh); }
+                            gs += __shfl_xor_sync(0xffffffffu, gs, 16); gq += __shfl_xor_sync(0xffffffffu, gq, 16);
+                            if ((lane & 23) == 0 && n0 < g.N) {        // lanes 0 and 8
+                                double* dst = g.gn_stats_out + ((size_t)n0 * (g.Cout >> 5) + (o >> 5)) * 2;
+                                atomicAdd(dst, (double)gs);
+                                atomicAdd(dst + 1, (double)gq);
+                            }
                         }
                     }
                 }
@@ -584,7 +600,8 @@ Tc2Plan plan_tc2(const ConvGeom& g) {
     while (t.TN > 1 && t.TN * t.HHt * t.HWd > 208) t.TN >>= 1;
     t.halo_rows = t.TN * t.HHt * t.HWd;
     if (t.halo_rows > 208) return fail("halo tile too large for shared memory");
-    if (g.y2_ptrs && t.TN != 1) return fail("per-sample output pointers need samples of at least one whole pixel tile (OH*OW >= 128)");
+    if ((g.y2_ptrs || g.gn_stats_out) && t.TN != 1)
+        return fail("per-sample output pointers / epilogue GroupNorm statistics need samples of at least one whole pixel tile (OH*OW >= 128)");
     if (t.HWd > 256 || t.HHt > 256 || t.TN > 256) return fail("TMA box dim");
     t.box_bytes = (t.halo_rows * 128 + 1023) & ~1023;
     t.halo_stage_bytes = 2 * t.box_bytes;
@@ -608,7 +625,7 @@ Tc2Plan plan_tc2(const ConvGeom& g) {
         const int items = t.m_groups * t.n_tiles, slots = mn_num_sms() / t.cs;
         while (t.ksplit * 2 * items <= slots && t.cblocks % (t.ksplit * 2) == 0 && t.cblocks / (t.ksplit * 2) >= 1 && t.ksplit < 8) t.ksplit *= 2;
         while (t.ksplit > 1 && (int64_t)t.ksplit * g.M * g.Cout * 4 > g.ws_bytes) t.ksplit >>= 1;
-        if (t.ksplit > 1 && (!g.ws || g.gn_mr || (g.Cout & 3) || g.y2_ptrs)) t.ksplit = 1;
+        if (t.ksplit > 1 && (!g.ws || g.gn_mr || (g.Cout & 3) || g.y2_ptrs || g.gn_stats_out)) t.ksplit = 1;
     }
     t.cbps = t.cblocks / t.ksplit;
     // cta_group::2 pairs (see the kernel): default whenever the cluster has 2 CTAs; MN_TC_CG=1 forces the cta_group::1 + multicast path

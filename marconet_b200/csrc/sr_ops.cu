@@ -404,6 +404,16 @@ extern "C" int mn_groupnorm_stats(const float* x, int x_cs, int N, int H, int W,
     return MN_OK;
 }
 
+extern "C" int mn_groupnorm_finalize(const double* stats_ws, int N, int H, int W, int C, int cpg, float eps, const int32_t* valid_w,
+                                     float* mean_rstd, void* stream) {
+    MN_REQUIRE(stats_ws && mean_rstd && N > 0 && H > 0 && W > 0 && C > 0 && cpg == 32 && C % 32 == 0, "mn_groupnorm_finalize: bad args");
+    const int G = C / cpg;
+    MN_CUDA_CHECK((mn_launch(gn_finalize_kernel, dim3(mn_cdiv(N * G, 128)), dim3(128), 0, (cudaStream_t)stream, stats_ws,
+                             reinterpret_cast<float2*>(mean_rstd), N, G, H, W, cpg, eps, valid_w)));
+    MN_LAUNCH_CHECK();
+    return MN_OK;
+}
+
 extern "C" int mn_groupnorm_apply(const float* x, int x_cs, float* y, int y_cs, const float* gamma, const float* beta,
                                   const float* mean_rstd, int N, int H, int W, int C, int cpg, int swish,
                                   const int32_t* valid_w, void* stream) {

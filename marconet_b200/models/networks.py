@@ -534,13 +534,15 @@ class ResTextBlockV2(nn.Module):
         return d
 
 
-def _res_block(pk, x, valid_w=None):
-    """GN -> swish -> conv -> GN -> swish -> conv (+ 1x1 skip), reference networks.py:506-516."""
+def _res_block(pk, x, valid_w=None, mr1=None):
+    """GN -> swish -> conv -> GN -> swish -> conv (+ 1x1 skip), reference networks.py:506-516.
+    ``mr1``: statistics of x when the convolution that produced x already accumulated them in its epilogue."""
     # GroupNorm statistics are a separate (read-only) pass; normalise + swish runs as mn_groupnorm_apply before the conv unless
     # ops.FUSE_GN routes it into the tcgen05 kernel's operand-split stage (measured slower with 4 split warps; off by default)
-    mr1 = ops.groupnorm_stats(x, valid_w=valid_w)
-    h = ops.conv2d(x, pk["c1"][0], 3, 3, pad=(1, 1), bias=pk["c1"][1], valid_w=valid_w, gn=(mr1,) + tuple(pk["n1"]))
-    mr2 = ops.groupnorm_stats(h, valid_w=valid_w)
+    if mr1 is None:
+        mr1 = ops.groupnorm_stats(x, valid_w=valid_w)
+    # the statistics of h (input of norm2) are accumulated by the epilogue of the conv that writes h: no separate read pass
+    h, mr2 = ops.conv2d(x, pk["c1"][0], 3, 3, pad=(1, 1), bias=pk["c1"][1], valid_w=valid_w, gn=(mr1,) + tuple(pk["n1"]), gn_stats=True)
     skip = x if pk["co"] is None else ops.conv2d(x, pk["co"][0], 1, 1, bias=pk["co"][1], valid_w=valid_w)
     return ops.conv2d(h, pk["c2"][0], 3, 3, pad=(1, 1), bias=pk["c2"][1], residual=skip, valid_w=valid_w, gn=(mr2,) + tuple(pk["n2"]))
 
@@ -794,8 +796,8 @@ class TSPSRNet(_PackedModule):
             s32 = self._fuse(pk, 32, s32, p32, locs_host, counts, 16)
 
         u = ops.resample_modulate(s32, None, up=True)
-        x = ops.conv2d(u, pk["up_1"][0], 3, 3, pad=(1, 1), bias=pk["up_1"][1], act=ACT_LRELU02)
-        x = _res_block(pk["up_res"], x)
+        x, mr = ops.conv2d(u, pk["up_1"][0], 3, 3, pad=(1, 1), bias=pk["up_1"][1], act=ACT_LRELU02, gn_stats=True)
+        x = _res_block(pk["up_res"], x, mr1=mr)
         s64 = ops.conv2d(x, pk["up_4"][0], 3, 3, pad=(1, 1), bias=pk["up_4"][1])
 
         if sum(counts) > 0:
@@ -803,8 +805,8 @@ class TSPSRNet(_PackedModule):
 
         x = ops.conv2d(s64, pk["fin_0"][0], 3, 3, pad=(1, 1), bias=pk["fin_0"][1], act=ACT_LRELU02)
         u = ops.resample_modulate(x, None, up=True)
-        x = ops.conv2d(u, pk["fin_3"][0], 3, 3, pad=(1, 1), bias=pk["fin_3"][1], act=ACT_LRELU02)
-        x = _res_block(pk["fin_res"], x)
+        x, mr = ops.conv2d(u, pk["fin_3"][0], 3, 3, pad=(1, 1), bias=pk["fin_3"][1], act=ACT_LRELU02, gn_stats=True)
+        x = _res_block(pk["fin_res"], x, mr1=mr)
         out = ops.conv2d(x, pk["fin_6"][0], 3, 3, pad=(1, 1), bias=pk["fin_6"][1], act=ACT_TANH)
         return ops.as_nchw_view(out)
 

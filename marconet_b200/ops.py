@@ -334,12 +334,15 @@ TC_MIN_FLOP = 3.0e7    # tiny launches are latency-bound either way and stay on 
 
 def conv2d(x, w, kh, kw, stride=(1, 1), pad=(0, 0), bias=None, out_scale=None, residual=None,
            res_broadcast=False, act=ACT_NONE, gain=1.0, out=None, out2=None, y2_scale=None,
-           valid_w=None, precision=None, want_y=True, split_k=0, gn=None, gn_fuse=None, out2_ptrs=None):
+           valid_w=None, precision=None, want_y=True, split_k=0, gn=None, gn_fuse=None, out2_ptrs=None, gn_stats=False):
     """mn_conv2d_nhwc.  ``w`` is the packed [KH*KW*Cin, Cout] matrix.  Returns y (or (y, y2)).
     ``gn=(mean_rstd, gamma, beta)``: the conv input is swish(GroupNorm(x)); fused into the tcgen05 v2 kernel's operand-split
     stage when ``gn_fuse`` is true and that kernel runs the layer, otherwise applied by mn_groupnorm_apply first.
-    (Measured on B200: with 4 split warps per CTA the fused transform makes the split stage the bottleneck -- 11.6 vs
-    10.1 ms per line -- so the default policy FUSE_GN is off; the kernel path stays tested for a wider split stage.)"""
+    (Measured on B200: with 4 split warps per CTA the fused transform makes the split stage the bottleneck -- 8.7 vs 7.1 ms per
+    line in round 2 -- so the default policy FUSE_GN is off; the kernel path stays tested for a wider split stage.)
+    ``gn_stats=True``: also return the GroupNorm statistics (mean / rstd [N, Cout/32, 2]) of the OUTPUT, for the GroupNorm that
+    follows this conv (networks.py:508-512): accumulated by the tcgen05 kernel's epilogue (mn_conv_params.gn_stats_out, no read
+    pass over y) when that kernel runs the layer, by mn_groupnorm_stats otherwise.  Returns (y, mean_rstd)."""
     global LAUNCHES
     lib = _lib.load()
     n, h, wd, cin, x_cs = nhwc_info(x, "x")
@@ -415,6 +418,10 @@ def conv2d(x, w, kh, kw, stride=(1, 1), pad=(0, 0), bias=None, out_scale=None, r
             prec = PREC_FP32_SIMT
             _note_fallback(cw, (n, h, wd, cin, cout, kh, kw, stride), 2.0 * n * oh * ow * cout * kh * kw * cin, p)
     p.precision = prec
+    stats_ws = None
+    if gn_stats and prec != PREC_FP32_SIMT and ver == 2 and oh * ow >= 128 and cout % 32 == 0 and y is not None and out2_ptrs is None:
+        stats_ws = torch.zeros((n * (cout // 32) * 2,), dtype=torch.float64, device=x.device)
+        p.gn_stats_out = stats_ws.data_ptr()
     if gn is not None and not gn_fused:      # no fused kernel for this layer: normalise into a temporary first
         xg = groupnorm_apply(x, gn[0], gn[1], gn[2], valid_w=valid_w)
         p.x = xg.data_ptr(); p.x_cs = xg.shape[3]
@@ -436,6 +443,14 @@ def conv2d(x, w, kh, kw, stride=(1, 1), pad=(0, 0), bias=None, out_scale=None, r
                 rec.setdefault(name, []).append(torch.nan_to_num((got - ref).abs().max() / scale, nan=float("inf")))
         finally:
             _TLS.calib = calib
+    if gn_stats:
+        if stats_ws is not None:
+            mr = torch.empty((n, cout // 32, 2), dtype=torch.float32, device=x.device)
+            _lib.check(lib.mn_groupnorm_finalize(_ptr(stats_ws), n, oh, ow, cout, 32, 1e-6, _ptr(valid_w), _ptr(mr), _stream()), "mn_groupnorm_finalize")
+            LAUNCHES += 2
+        else:
+            mr = groupnorm_stats(y, valid_w=valid_w)
+        return y, mr
     if y2 is not None:
         return (y, y2) if want_y else y2
     return y

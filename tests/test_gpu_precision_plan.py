@@ -201,3 +201,30 @@ def test_reference_helper_functions():
     bm, bv = b.view(2, 7, -1).mean(2).view(2, 7, 1, 1), (b.view(2, 7, -1).var(2) + 1e-5).sqrt().view(2, 7, 1, 1)
     am, av = a.view(2, 7, -1).mean(2).view(2, 7, 1, 1), var.sqrt().view(2, 7, 1, 1)
     assert torch.allclose(out, (a - am) / av * bv + bm, atol=1e-5)
+
+
+@pytest.mark.parametrize("masked", [False, True])
+def test_groupnorm_statistics_accumulated_in_the_conv_epilogue(masked):
+    """mn_conv_params.gn_stats_out: the producing conv's epilogue accumulates sum / sum of squares per (sample, 32-channel group) of
+    its output; finalised statistics must equal the separate read pass (mn_groupnorm_stats) over the stored tensor."""
+    from marconet_b200 import ops
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(17)
+    n, h, w, cin, cout = 5, 32, 32, 128, 256
+    x = torch.randn(n, h, w, cin, generator=g).to(dev)
+    w4 = (torch.randn(cout, cin, 3, 3, generator=g) / 34.0).to(dev)
+    bias = torch.randn(cout, generator=g).to(dev)
+    cw = _packed(w4, f"test.gn_stats_{masked}")
+    vw = torch.tensor([32, 7, 19, 32, 1], dtype=torch.int32, device=dev) if masked else None
+    y, mr = ops.conv2d(x, cw, 3, 3, pad=(1, 1), bias=bias, act=ops.ACT_LRELU02, valid_w=vw, gn_stats=True)
+    ref = ops.groupnorm_stats(y, valid_w=vw)
+    torch.cuda.synchronize()
+    assert mr.shape == ref.shape == (n, cout // 32, 2)
+    err_mean = (mr[..., 0] - ref[..., 0]).abs().max().item()
+    err_rstd = ((mr[..., 1] - ref[..., 1]).abs() / ref[..., 1].abs()).max().item()
+    print("epilogue GN statistics vs read pass: mean abs err", err_mean, "rstd rel err", err_rstd)
+    assert err_mean < 1e-5 and err_rstd < 1e-5
+    # and the exact fp32 kernel (no fused statistics there) takes the separate pass transparently
+    y0, mr0 = ops.conv2d(x, cw, 3, 3, pad=(1, 1), bias=bias, act=ops.ACT_LRELU02, valid_w=vw, gn_stats=True, precision=ops.PREC_FP32_SIMT)
+    assert (mr0[..., 0] - ref[..., 0]).abs().max().item() < 1e-3
+    ops.PLAN.pop(cw.name, None)

@@ -76,16 +76,16 @@ def main():
                 s32 = sr._fuse(spk, 32, s32, p32, locs.cpu(), counts, 16)
             with Sec("sr.conv_up"):
                 u = ops.resample_modulate(s32, None, up=True)
-                x = ops.conv2d(u, spk["up_1"][0], 3, 3, pad=(1, 1), bias=spk["up_1"][1], act=ops.ACT_LRELU02)
-                x = _res_block(spk["up_res"], x)
+                x, mr = ops.conv2d(u, spk["up_1"][0], 3, 3, pad=(1, 1), bias=spk["up_1"][1], act=ops.ACT_LRELU02, gn_stats=True)
+                x = _res_block(spk["up_res"], x, mr1=mr)
                 s64 = ops.conv2d(x, spk["up_4"][0], 3, 3, pad=(1, 1), bias=spk["up_4"][1])
             with Sec("sr.fuse64"):
                 s64 = sr._fuse(spk, 64, s64, ops.as_nhwc(f64), locs.cpu(), counts, 32)
             with Sec("sr.conv_final"):
                 x = ops.conv2d(s64, spk["fin_0"][0], 3, 3, pad=(1, 1), bias=spk["fin_0"][1], act=ops.ACT_LRELU02)
                 u = ops.resample_modulate(x, None, up=True)
-                x = ops.conv2d(u, spk["fin_3"][0], 3, 3, pad=(1, 1), bias=spk["fin_3"][1], act=ops.ACT_LRELU02)
-                x = _res_block(spk["fin_res"], x)
+                x, mr = ops.conv2d(u, spk["fin_3"][0], 3, 3, pad=(1, 1), bias=spk["fin_3"][1], act=ops.ACT_LRELU02, gn_stats=True)
+                x = _res_block(spk["fin_res"], x, mr1=mr)
                 out = ops.conv2d(x, spk["fin_6"][0], 3, 3, pad=(1, 1), bias=spk["fin_6"][1], act=ops.ACT_TANH)
         return out
 
