@@ -21,7 +21,7 @@
 //     MMA warp is released after ~1k cycles), stage through shared memory and store with fully coalesced float4 rows,
 //     while the feed + MMA warps are already working on tile i+1.
 // Warp roles: 0 = weight (B) TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = TMEM feed,
-//             6 = halo TMA producer, 7..10 = split (fp32 halo -> hi/lo fp16 halo) + epilogue.
+//             6 = halo TMA producer, 7..10 = split (fp32 halo -> hi/lo fp16 halo), 11..14 = epilogue (round 2: its own warps).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -35,7 +35,7 @@ namespace {
 using namespace tcptx;
 
 constexpr int KB = 64;
-constexpr int NUM_THREADS2 = 352;
+constexpr int NUM_THREADS2 = 480;               // 15 warps: see the role list in the header comment
 constexpr int A_STAGES = 4;
 constexpr int MAX_BSTAGES = 4;
 constexpr int STG_COLS = 64;
@@ -349,7 +349,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         };
         // The epilogue of tile i runs after the first two halo tiles of tile i+1 have been split, so the feed/MMA warps have
         // ~2 x taps k-blocks of work queued while these warps drain TMEM and store tile i.
-        const int epi_after_cb = t.epi_cb;
+        if (warp >= 11) {
+            // ======================= dedicated epilogue warps (11..14: warp & 3 = 3,0,1,2 -> the four TMEM lane quarters) =======================
+            // Round 2: the four split warps used to run the epilogue as well and were the co-bottleneck of every tile with a short K
+            // loop (ncu source page: 27 % of all stall samples in the row-store loop on 128->128 @128x128 against 5 % in the split);
+            // 122 registers per thread at 480 threads, no spills.
+            for (int work = cluster_id; work < total_work; work += num_clusters) epilogue(work);
+        } else {
         int prev_work = -1;
         uint32_t hs = 0, hph = 0;
         constexpr bool gn = GN;       // fused GroupNorm(+swish) input transform: separate instantiation, zero cost when off
@@ -431,12 +437,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // these generic writes precede the next TMA refill
                 mbar_arrive(bar(I_SD + hs));
                 if (++hs == (uint32_t)HS) { hs = 0; hph ^= 1; }
-                if (cbi == epi_after_cb && prev_work >= 0) epilogue(prev_work);
+                (void)prev_work;
             }
             prev_work = work;
         }
-        if (prev_work >= 0) epilogue(prev_work);
         conv_range_report(g, __float_as_uint(amax), t.prec == MN_PREC_F16X3_TC || t.prec == MN_PREC_F16X1_TC);
+        }
     } else if (warp == 1) {
       if (CG == 1 || crank == 0) {
         // =========================== MMA issuer (whole warp converged, one elected lane issues) ===========================
