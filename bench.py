@@ -328,7 +328,10 @@ def run_ours(args):
         roof = modconv_roofline(nets["tspgan"], chars, dev) if rank == 0 else None
         collective = None
         if not args.no_collective:
-            collective = collective_record(nets, world, rank, dev, args)
+            try:
+                collective = collective_record(nets, world, rank, dev, args)
+            except Exception as exc:      # the sub-records must never cost the headline line
+                collective = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
         # informational: end to end through GraphedLines (this repo's own extension API) with the same host buffers and copies.
         # Single process only (no collectives inside, so a failure here cannot desynchronise ranks); runs last.
