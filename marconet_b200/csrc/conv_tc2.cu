@@ -616,7 +616,9 @@ Tc2Plan plan_tc2(const ConvGeom& g) {
     t.cblocks = g.Cin / KB; t.taps = g.KH * g.KW;
     // 128-wide channel tiles unless that leaves most SMs idle (small-M layers at batch 1: ResNet 8x512 maps, 8x8 / 16x16
     // generator layers): then 64-wide tiles double the number of work items.
-    p.NT = (g.Cout % 128 == 0 && (int64_t)((t.m_tiles + 1) / 2) * (g.Cout / 128) * 2 >= 120) ? 128 : 64;
+    static int nt_items = -1;       // developer knob: CTAs a 128-wide tiling must keep busy (MN_TC_NT_ITEMS, default 120)
+    if (nt_items < 0) { const char* e = getenv("MN_TC_NT_ITEMS"); nt_items = e ? atoi(e) : 120; }
+    p.NT = (g.Cout % 128 == 0 && (int64_t)((t.m_tiles + 1) / 2) * (g.Cout / 128) * 2 >= nt_items) ? 128 : 64;
     t.n_tiles = g.Cout / p.NT;
     static int force_cs = -1;
     if (force_cs < 0) { const char* e = getenv("MN_TC_CLUSTER"); force_cs = e ? atoi(e) : 0; }
