@@ -150,9 +150,32 @@ class _PackedModule(nn.Module):
         if self._packed is None or self._packed_key != key:
             with torch.no_grad():
                 self._packed = self._pack(device)
+                self._pack_tc_planes(self._packed)
             self._packed_key = key
             self._mg, self._mg_hits = None, {}          # captured graphs hold the old packed weights
         return self._packed
+
+    @staticmethod
+    def _pack_tc_planes(packed):
+        """Split the tensor-core layers' weights into their hi/lo 16-bit planes NOW, on the packing stream (a lazy first
+        touch would run the pack kernels on whichever stream -- or graph capture -- happens to use the layer first)."""
+        prec = ops.default_precision()
+        if prec == ops.PREC_FP32_SIMT:
+            return
+
+        def walk(o):
+            if isinstance(o, ops.ConvWeight):
+                p = o.precision if o.precision is not None else prec
+                if o.tc_capable() and p != ops.PREC_FP32_SIMT:
+                    o.tc(p)
+            elif isinstance(o, dict):
+                for v in o.values():
+                    walk(v)
+            elif isinstance(o, (list, tuple)):
+                for v in o:
+                    walk(v)
+
+        walk(packed)
 
     @staticmethod
     def _need_cuda(t, what):
@@ -769,12 +792,14 @@ class TSPSRNet(_PackedModule):
             l64, l32, o = [], [], 0
             for n in counts:
                 l64.append(p64_[o:o + n].permute(0, 3, 1, 2)); l32.append(p32_[o:o + n].permute(0, 3, 1, 2)); o += n
-            return (self._forward(lq_, l64[:len(priors64)], l32[:len(priors32)], locs_, None),)
+            return (self._forward(lq_, l64[:len(priors64)], l32[:len(priors32)], locs_, None, _trunk_side=self._mg_side(lq_.device)),)
 
         key = ("sr", tuple(lq.shape), tuple(counts), len(priors64), tuple(locs.shape), lq.device)
         return self._mg_run(key, specs, run, fill)
 
-    def _forward(self, lq, priors64, priors32, locs, _trunk):
+    def _forward(self, lq, priors64, priors32, locs, _trunk, _trunk_side=None):
+        """``_trunk_side`` = (stream, split-K scratch): compute the LR trunk on that stream while this one converts the 32-px priors
+        (they are independent: networks.py:412-416 vs :424); joined before the first fuse stage.  Used inside recorded graphs."""
         dev = lq.device
         pk = self._get_packed(dev)
         d = self.dim
@@ -789,10 +814,25 @@ class TSPSRNet(_PackedModule):
         else:
             locs_host = locs.detach().to("cpu", torch.float32).contiguous()      # the one device->host round trip (reference: ~6 per character)
 
-        s32 = _trunk if _trunk is not None else self._trunk(pk, lq)
+        trunk_done = None
+        if _trunk is not None:
+            s32 = _trunk
+        elif _trunk_side is not None and sum(counts) > 0:
+            side, scratch = _trunk_side
+            main = torch.cuda.current_stream(dev)
+            side.wait_stream(main)
+            with torch.cuda.stream(side), ops.use_workspace(scratch):
+                s32 = self._trunk(pk, lq)
+                trunk_done = torch.cuda.Event()
+                trunk_done.record(side)
+            s32.record_stream(main)
+        else:
+            s32 = self._trunk(pk, lq)
 
         if sum(counts) > 0:
             p32 = _two(pk["conv_32_to256"], self._gather_priors(priors32, 512, 32))
+            if trunk_done is not None:
+                torch.cuda.current_stream(dev).wait_event(trunk_done)
             s32 = self._fuse(pk, 32, s32, p32, locs_host, counts, 16)
 
         u = ops.resample_modulate(s32, None, up=True)
