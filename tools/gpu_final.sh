@@ -1,0 +1,20 @@
+#!/bin/bash
+# Round-2 final evidence run (single B200): full GPU test suite incl. the staged unmodified reference scripts, smoke, bench with the
+# driver's arguments, configs[4] sweep, ncu launch list + full capture of the roofline kernel, compute-sanitizer over the new kernels.
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q -rA -p no:cacheprovider --timeout 600 > gpurun_out/r2_pytest_gpu_final.txt 2>&1
+echo "pytest rc=$?" >> gpurun_out/r2_pytest_gpu_final.txt
+timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_smoke.txt 2>&1
+echo "smoke rc=$?" >> gpurun_out/r2_smoke.txt
+timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/r2_bench_final.json 2> gpurun_out/r2_bench_final.err
+echo "bench rc=$?"
+timeout 300 python tools/bench_style_sweep.py --mode batched > gpurun_out/r2_style_sweep_batched.json 2> gpurun_out/r2_style_sweep.err
+timeout 300 python tools/bench_style_sweep.py --mode per_step > gpurun_out/r2_style_sweep_per_step.json 2>> gpurun_out/r2_style_sweep.err
+timeout 300 python tools/profile_sections.py > gpurun_out/r2_sections_final.json 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/r2_launches_step.csv python bench.py --profile --steps 1 --warmup 3 --no-collective > gpurun_out/r2_launches_step.out 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv_tc2_kernel -s 3 -c 1 -f -o gpurun_out/prof_r2_tc2_c512_final python tools/bench_conv.py 16 32 32 512 512 3 1 3 > /dev/null 2>&1
+timeout 900 compute-sanitizer --tool memcheck python tools/sanitize_round2_kernels.py > gpurun_out/r2_sanitizer_memcheck.txt 2>&1
+echo "memcheck rc=$?" >> gpurun_out/r2_sanitizer_memcheck.txt
+timeout 900 compute-sanitizer --tool racecheck python tools/sanitize_round2_kernels.py > gpurun_out/r2_sanitizer_racecheck.txt 2>&1
+echo "racecheck rc=$?" >> gpurun_out/r2_sanitizer_racecheck.txt
+tail -n 4 gpurun_out/r2_pytest_gpu_final.txt; tail -n 3 gpurun_out/r2_smoke.txt; tail -n 4 gpurun_out/r2_sanitizer_memcheck.txt; tail -n 4 gpurun_out/r2_sanitizer_racecheck.txt; cat gpurun_out/r2_sections_final.json | tail -n 1

@@ -23,7 +23,7 @@ for n, h, w, cin, cout in ((3, 32, 32, 64, 256), (1, 8, 16, 64, 64), (2, 16, 32,
         ops.conv2d(x, cw, 3, 3, pad=(1, 1), bias=bias, act=ops.ACT_LRELU02, gain=2 ** 0.5, valid_w=vw, precision=prec)
         ops.conv2d(x, cw, 3, 3, pad=(1, 1), bias=bias, out_scale=torch.rand(n, cout, device=dev), out2=True, y2_scale=torch.rand(n, cout, device=dev),
                    residual=torch.randn(n, h, w, cout, device=dev), act=ops.ACT_TANH, precision=prec)
-    if h * w >= 128:
+    if h * w >= 128 and 2.0 * n * h * w * cout * 9 * cin >= ops.TC_MIN_FLOP:     # layers the tensor-core kernel runs (peer pointers need it)
         ops.conv2d(x, cw, 3, 3, pad=(1, 1), bias=bias, valid_w=vw, gn_stats=True)
         # per-sample destination pointers of the second output (local memory standing in for a peer's)
         dst = torch.empty(n, h, w, cout, device=dev)
