@@ -52,6 +52,7 @@ struct Tc2Geom {
     int cblocks, taps, KW, ph, pw;
     int ksplit, cbps;   // split-K over channel blocks for layers with too few tiles: work = (tile, k-slice), cbps channel blocks each
     int bstages, cs, cg;
+    long long* trace;   // developer timeline (tools/trace_tc2.py): CTA 0 records (event, clock64) pairs; NULL in production
     int hstages;        // depth of the halo ring (2, or 3 when shared memory allows: layers with <= 2 channel blocks per tile
                         // otherwise stall every tile on the TMA latency of the next tile's second halo)
     int epi_cb;         // the split warps run the epilogue of tile i after splitting this channel block of tile i+1
@@ -136,6 +137,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
+    // timeline instrumentation (off unless mn_debug_tc2_trace installed a buffer): event e of role-lane `who` at clock64()
+    long long* const trace = (t.trace && blockIdx.x == 0) ? t.trace : nullptr;
+    auto mark = [&](int ev, int idx) {
+        if (trace) {
+            const unsigned slot = atomicAdd(reinterpret_cast<unsigned*>(trace), 1u);
+            if (slot < 4000u) { trace[1 + 2 * slot] = ((long long)ev << 32) | (unsigned)idx; trace[2 + 2 * slot] = clock64(); }
+        }
+    };
     auto tile_origin = [&](int work, int& n0, int& oy0, int& ox0) {
         int m_tile = work_mg(work) * cs + (int)crank;
         if (m_tile >= t.m_tiles) { n0 = g.N + 1024; oy0 = 0; ox0 = 0; return; }   // padding CTA of a cluster: everything out of bounds
@@ -188,6 +197,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             for (int cb = cb0; cb < cb0 + t.cbps; ++cb) {
                 mbar_wait(bar(I_HE + hs), ph ^ 1);
                 if (elect_one_sync()) {
+                    mark(1, work);                       // halo stage free -> TMA issue
                     mbar_expect_tx(bar(I_HF + hs), 2u * t.halo_rows * 128u);
                     const uint32_t dst = smem_base + hs * t.halo_stage_bytes;
                     tma_load_4d(&tmA, bar(I_HF + hs), dst, cb * KB, ox0 - t.pw, oy0 - t.ph, n0);
@@ -231,6 +241,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const uint32_t acc_st = ACC_ST == 2 ? (ecnt & 1) : 0u, acc_ph = ACC_ST == 2 ? ((ecnt >> 1) & 1) : (ecnt & 1);
             const uint32_t acc_addr = lane_addr + acc_st * 2 * NT;
             mbar_wait(bar(I_ACCF + acc_st), acc_ph);
+            if (r == 0) mark(8, work);                     // accumulators complete -> drain starts
             ++ecnt;
             tc_fence_after();
             constexpr int HALVES = NT / STG_COLS;
@@ -266,6 +277,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             drain(0, false);
             if (HALVES > 1) drain(1, true);
             tc_fence_before();
+            if (r == 0) mark(9, work);                           // drain done
             if (CG == 2) {                                       // one arrival per warp, on the LEADER's barrier (it issues the pair's MMAs)
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(mapa_u32(bar(I_ACCE + acc_st), 0));
@@ -308,8 +320,33 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             if (g.y2_ptrs) y2base = g.y2_ptrs[n0] - (size_t)n0 * g.OH * g.OW * g.y2_cs;
                         }
                         float gs = 0.f, gq = 0.f;       // GroupNorm statistics of this thread's 16 rows x 4 channels (one group)
+                        // One sample per tile and the tile inside the tensor (the plan guarantees H % TH == 0, W % TW == 0): every row is
+                        // valid and its pixel index is arithmetic -- no rowm look-ups, no per-row branch, so the unrolled iterations overlap
+                        // (the branchy loop serialised three dependent shared-memory loads per row: ~9k cycles per 64-column half,
+                        // the limiter of the 64-wide tiles, tools/trace_tc2.py).
+                        const bool dense_tile = one_n && n0 < g.N;
+                        const int tws = __ffs(t.TW) - 1;
+                        const int m00 = (n0 * g.OH + oy0) * g.OW + ox0;
+                        const int vwn = (dense_tile && g.valid_w) ? g.valid_w[n0] : 0x7fffffff;
+                        auto rows_dense = [&](auto tag) {
+                            constexpr int ACT = decltype(tag)::value;
+#pragma unroll 8
+                            for (int i = 0; i < 16; ++i) {
+                                const int row = q * 32 + i * 2 + (lane >> 4);
+                                const int th = row >> tws, tw = row & (t.TW - 1);
+                                const int m = m00 + th * g.OW + tw;
+                                const float4 u = *reinterpret_cast<const float4*>(stg + row * STG_PITCH + col);
+                                const float4 w4 = conv_epilogue_row4<ACT>(g, m, n0, ox0 + tw >= vwn, o, u, bias4, true, os4, true, y2s4, y2base);
+                                if (g.gn_stats_out) {
+                                    gs += (w4.x + w4.y) + (w4.z + w4.w);
+                                    gq = fmaf(w4.x, w4.x, fmaf(w4.y, w4.y, fmaf(w4.z, w4.z, fmaf(w4.w, w4.w, gq))));
+                                }
+                            }
+                        };
                         auto rows = [&](auto tag) {
                             constexpr int ACT = decltype(tag)::value;
+                            if (dense_tile) { rows_dense(tag); return; }
+                            if (one_n) return;                       // padding CTA of a cluster: nothing to store
 #pragma unroll 4
                             for (int i = 0; i < 16; ++i) {
                                 const int row = q * 32 + i * 2 + (lane >> 4);
@@ -346,6 +383,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 }
                 named_bar_sync(1, 128);
             }
+            if (r == 0) mark(10, work);                          // tile stored
         };
         // The epilogue of tile i runs after the first two halo tiles of tile i+1 have been split, so the feed/MMA warps have
         // ~2 x taps k-blocks of work queued while these warps drain TMEM and store tile i.
@@ -373,6 +411,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     named_bar_sync(2, 128);
                 }
                 mbar_wait(bar(I_HF + hs), hph);
+                if (sidx == 0) mark(2, work);            // halo landed -> split starts
                 uint8_t* halo = smem + hs * t.halo_stage_bytes;
                 for (int rho = sidx; rho < t.halo_rows; rho += 128) {
                     uint8_t* row0 = halo + rho * 128;
@@ -435,6 +474,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // these generic writes precede the next TMA refill
+                if (sidx == 0) mark(3, work);            // split done
                 mbar_arrive(bar(I_SD + hs));
                 if (++hs == (uint32_t)HS) { hs = 0; hph ^= 1; }
                 (void)prev_work;
@@ -456,6 +496,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const uint32_t acc_st = ACC_ST == 2 ? (tcnt & 1) : 0u, acc_ph = ACC_ST == 2 ? ((tcnt >> 1) & 1) : (tcnt & 1);
             const uint32_t d_addr = tmem_base + acc_st * 2 * NT;
             mbar_wait(bar(I_ACCE + acc_st), acc_ph ^ 1);   // epilogue has drained this accumulator stage
+            if (lane == 0) mark(6, work);                  // accumulator free -> MMAs of this tile may start
             tc_fence_after();
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait(bar(I_CD + as), aph);
@@ -494,7 +535,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (++as == A_STAGES) { as = 0; aph ^= 1; }
                 if (++bs == (uint32_t)BS) { bs = 0; bph ^= 1; }
             }
-            if (elect_one_sync()) { if (CG == 2) tc_commit_mc_cg2(bar(I_ACCF + acc_st), cmask); else tc_commit(bar(I_ACCF + acc_st)); }
+            if (elect_one_sync()) { mark(7, work); if (CG == 2) tc_commit_mc_cg2(bar(I_ACCF + acc_st), cmask); else tc_commit(bar(I_ACCF + acc_st)); }   // last MMA of the tile issued
             __syncwarp();
         }
       }
@@ -511,6 +552,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int work = cluster_id; work < total_work; work += num_clusters) {
             for (int cb = 0; cb < t.cbps; ++cb) {
                 mbar_wait(bar(I_SD + hs), hph);
+                if (r == 0) mark(4, work);               // split halo visible -> feed of this channel block starts
                 const uint8_t* halo = smem + hs * t.halo_stage_bytes;
                 int ky = 0, kx = 0;
                 for (int tap = 0; tap < t.taps; ++tap) {
@@ -544,6 +586,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     }
                     if (++as == A_STAGES) { as = 0; aph ^= 1; }
                 }
+                if (r == 0) mark(5, work);               // all taps of this channel block fed
                 mbar_arrive(bar(I_HE + hs));         // all taps of this channel block have been read
                 if (++hs == (uint32_t)HS) { hs = 0; hph ^= 1; }
             }
@@ -573,6 +616,8 @@ PFN_encodeTiled get_encode2() {
     }
     return fn;
 }
+
+long long* g_tc2_trace = nullptr;      // mn_debug_tc2_trace
 
 struct Tc2Plan { bool ok; const char* why; int NT; int smem; Tc2Geom t; };
 
@@ -695,6 +740,10 @@ int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mbh, const CUtensorMap&
 
 }  // namespace
 
+// Developer hook (tools/trace_tc2.py): device buffer of 1 + 2*4000 int64 -- [0] = event counter (zero it), then (event<<32 | work,
+// clock64) pairs recorded by CTA 0 of every conv_tc2 launch while installed.  NULL uninstalls.  Not part of the product API.
+extern "C" int mn_debug_tc2_trace(long long* device_buffer) { g_tc2_trace = device_buffer; return 0; }
+
 int mn_conv_tc2_supported(const ConvGeom& g, const char** why) {
     Tc2Plan p = plan_tc2(g);
     if (why) *why = p.ok ? "" : p.why;
@@ -732,6 +781,7 @@ int mn_conv_tc2_launch(const ConvGeom& g, const void* w_hi, const void* w_lo, co
     }
     t.wscale = w_scale + 1;
     t.prec = prec;
+    t.trace = g_tc2_trace;
     int rc;
     if (t.cg == 2) {
         if (g.gn_mr) rc = p.NT == 128 ? launch_tc2<128, true, 2>(ma, mbh, mbl, g, p, st) : launch_tc2<64, true, 2>(ma, mbh, mbl, g, p, st);
