@@ -20,8 +20,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_igemm_f32_kernel(const ConvG
     mn_pdl_prologue();
     constexpr int TN = BN / 16;       // columns per thread (8 or 4)
     constexpr int NS = TN / 4;        // float4 strips per thread along N
-    __shared__ __align__(16) float As[2][BK][BM];
-    __shared__ __align__(16) float Bs[2][BK][BN];
+    // one buffer: the A / B k-tiles during the K loop, then the staging area of the epilogue (64 rows x BN floats fit exactly)
+    __shared__ __align__(16) float smem_buf[2 * BK * BM + 2 * BK * BN];
+    float (*As)[BK][BM] = reinterpret_cast<float (*)[BK][BM]>(smem_buf);
+    float (*Bs)[BK][BN] = reinterpret_cast<float (*)[BK][BN]>(smem_buf + 2 * BK * BM);
+    static_assert(2 * BK * BM + 2 * BK * BN >= 64 * BN, "staging half-tile must fit");
 
     const int tid = threadIdx.x;
     const int m0 = blockIdx.x * BM;
@@ -152,20 +155,44 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_igemm_f32_kernel(const ConvG
     }
 
     // ---- epilogue ----
+    // The accumulator tile goes through shared memory in two 64-row halves and ONE rolled loop runs the fused epilogue.  (Round 1
+    // called the generic epilogue from the fully unrolled 8 x NS register loop: 7k .. 14k straight-line SASS instructions, each
+    // executed once per warp -- the small layers this kernel serves spent their time on instruction-cache misses: 28 .. 70 us for
+    // microseconds of arithmetic, ncu source page profiles/r2_simt_epilogue_before.txt.)
+    const bool vec_ok = (g.Cout & 3) == 0 && (!g.y || ((g.y_cs & 3) == 0 && (reinterpret_cast<uintptr_t>(g.y) & 15) == 0)) &&
+                        (!g.y2 || ((g.y2_cs & 3) == 0 && (reinterpret_cast<uintptr_t>(g.y2) & 15) == 0)) &&
+                        (!g.residual || ((g.res_cs & 3) == 0 && (reinterpret_cast<uintptr_t>(g.residual) & 15) == 0)) &&
+                        (!g.out_scale || ((g.os_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(g.out_scale) & 15) == 0)) &&
+                        (!g.y2_scale || ((g.y2s_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(g.y2_scale) & 15) == 0)) &&
+                        (!g.bias || (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0) && (g.splits <= 1 || (reinterpret_cast<uintptr_t>(g.ws) & 15) == 0);
+    const int hw = g.OH * g.OW;
+    float* stg = smem_buf;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int m = m0 + (i >> 2) * 64 + ty * 4 + (i & 3);
-        if (m >= g.M) continue;
+    for (int half = 0; half < 2; ++half) {
+        if (half) __syncthreads();            // the first half has been read (the K loop ends with a barrier of its own)
 #pragma unroll
-        for (int s = 0; s < NS; ++s) {
-            const int o = n0 + s * (BN / NS) + tx * 4;
-            if (o >= g.Cout) continue;
-            float v[4] = {acc[i][s * 4], acc[i][s * 4 + 1], acc[i][s * 4 + 2], acc[i][s * 4 + 3]};
+        for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+            for (int s = 0; s < NS; ++s)
+                *reinterpret_cast<float4*>(&stg[(ty * 4 + ii) * BN + s * (BN / NS) + tx * 4]) =
+                    make_float4(acc[half * 4 + ii][s * 4], acc[half * 4 + ii][s * 4 + 1], acc[half * 4 + ii][s * 4 + 2], acc[half * 4 + ii][s * 4 + 3]);
+        __syncthreads();
+#pragma unroll 1
+        for (int idx = tid; idx < 64 * (BN / 4); idx += NTHREADS) {
+            const int row = idx / (BN / 4), c4 = idx - row * (BN / 4);
+            const int m = m0 + half * 64 + row, o = n0 + c4 * 4;
+            if (m >= g.M || o >= g.Cout) continue;
+            const float4 u = *reinterpret_cast<const float4*>(&stg[row * BN + c4 * 4]);
             if (g.splits > 1) {
                 float* dst = g.ws + ((size_t)split * g.M + m) * g.Cout + o;
-                if (o + 3 < g.Cout && (g.Cout & 3) == 0) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-                else for (int j = 0; j < 4 && o + j < g.Cout; ++j) dst[j] = v[j];
+                if (vec_ok) *reinterpret_cast<float4*>(dst) = u;
+                else { const float v[4] = {u.x, u.y, u.z, u.w}; for (int j = 0; j < 4 && o + j < g.Cout; ++j) dst[j] = v[j]; }
+            } else if (vec_ok) {
+                const int n = m / hw;
+                const bool masked = g.valid_w && (m % g.OW) >= g.valid_w[n];
+                conv_epilogue_vec4(g, m, n, masked, o, u, g.bias ? ldg4(g.bias + o) : make_float4(0.f, 0.f, 0.f, 0.f));
             } else {
+                float v[4] = {u.x, u.y, u.z, u.w};
                 conv_epilogue4(g, m, o, v);
             }
         }

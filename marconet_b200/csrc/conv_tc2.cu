@@ -139,10 +139,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
     // timeline instrumentation (off unless mn_debug_tc2_trace installed a buffer): event e of role-lane `who` at clock64()
     long long* const trace = (t.trace && blockIdx.x == 0) ? t.trace : nullptr;
+    // Fixed slots, plain stores (an atomic slot counter stalls the marking warp for an L2 round trip per event and distorts the
+    // timeline): tile iteration `it` of this CTA owns 64 int64s; events 1..15 at [it*64 + ev], per-k-block events ev >= 16 at
+    // [it*64 + ev] (the caller adds the k-block index, < 24).
     auto mark = [&](int ev, int idx) {
         if (trace) {
-            const unsigned slot = atomicAdd(reinterpret_cast<unsigned*>(trace), 1u);
-            if (slot < 4000u) { trace[1 + 2 * slot] = ((long long)ev << 32) | (unsigned)idx; trace[2 + 2 * slot] = clock64(); }
+            const int it = (idx - cluster_id) / num_clusters;
+            if (it < 64 && ev < 64) trace[1 + it * 64 + ev] = clock64();
         }
     };
     auto tile_origin = [&](int work, int& n0, int& oy0, int& ox0) {
@@ -231,6 +234,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const int nt_i = work_nt(work);
             const int ks = work_ks(work);
             int n0, oy0, ox0;
+            if (r == 0) mark(13, work);                    // epilogue loop top
             tile_origin(work, n0, oy0, ox0);
             {
                 const int n = n0 + tn, oy = oy0 + th, ox = ox0 + tw;
@@ -294,6 +298,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                              keep[(HALVES > 1) ? 4 * i + 3 : 0]);
                 }
                 named_bar_sync(1, 128);
+                if (r == 0) mark(11, work);                      // staging complete (all four warps drained)
                 {
                     const int col = (lane & 15) * 4;
                     const int o = nt_i * NT + half * STG_COLS + col;
@@ -368,6 +373,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             case MN_ACT_LRELU02: rows(ActTag<MN_ACT_LRELU02>{}); break;
                             default: rows(ActTag<-1>{}); break;
                         }
+                        if (r == 0) mark(12, work);              // rows stored (this warp)
                         if (g.gn_stats_out) {
                             // lanes 0-7 / 8-15 (and 16-23 / 24-31, the odd rows) hold the two 32-channel groups of this 64-column half
 #pragma unroll
@@ -554,14 +560,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 mbar_wait(bar(I_SD + hs), hph);
                 if (r == 0) mark(4, work);               // split halo visible -> feed of this channel block starts
                 const uint8_t* halo = smem + hs * t.halo_stage_bytes;
-                int ky = 0, kx = 0;
-                for (int tap = 0; tap < t.taps; ++tap) {
-                    const int rho = rho0 + ky * t.HWd + kx;
-                    if (++kx == t.KW) { kx = 0; ++ky; }
+                // Software-pipelined: the shared-memory reads of tap t+1 are issued right after the TMEM stores of tap t, so
+                // their latency hides behind tcgen05.wait::st + the arrive (the register WAR hazard is the scoreboard's job).
+                uint32_t hi[32], lo[32];
+                auto load_tap = [&](int rho) {
                     const uint8_t* hsrc = halo + rho * 128;
                     const uint8_t* lsrc = hsrc + t.box_bytes;
                     const int sw = rho & 7;
-                    uint32_t hi[32], lo[32];
 #pragma unroll
                     for (int jj = 0; jj < 8; ++jj) {
                         const uint4 a = *reinterpret_cast<const uint4*>(hsrc + ((jj ^ sw) << 4));
@@ -569,14 +574,24 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         hi[4 * jj] = a.x; hi[4 * jj + 1] = a.y; hi[4 * jj + 2] = a.z; hi[4 * jj + 3] = a.w;
                         lo[4 * jj] = b.x; lo[4 * jj + 1] = b.y; lo[4 * jj + 2] = b.z; lo[4 * jj + 3] = b.w;
                     }
+                };
+                int ky = 0, kx = 0;
+                load_tap(rho0);
+                for (int tap = 0; tap < t.taps; ++tap) {
                     mbar_wait(bar(I_AE + as), aph ^ 1);
+                    if (r == 0 && cb * t.taps + tap < 24) mark(16 + cb * t.taps + tap, work);          // A stage free
                     tc_fence_after();
                     const uint32_t a_dst = lane_addr + A_COL0 + as * 64;
 #pragma unroll
                     for (int c = 0; c < 4; ++c) tc_st8(a_dst + c * 8, hi + c * 8);
 #pragma unroll
                     for (int c = 0; c < 4; ++c) tc_st8(a_dst + 32 + c * 8, lo + c * 8);
+                    if (tap + 1 < t.taps) {
+                        if (++kx == t.KW) { kx = 0; ++ky; }
+                        load_tap(rho0 + ky * t.HWd + kx);
+                    }
                     tc_wait_st();
+                    if (r == 0 && cb * t.taps + tap < 24) mark(40 + cb * t.taps + tap, work);          // TMEM stores of this tap complete
                     tc_fence_before();
                     if (CG == 2) {
                         __syncwarp();
@@ -740,8 +755,8 @@ int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mbh, const CUtensorMap&
 
 }  // namespace
 
-// Developer hook (tools/trace_tc2.py): device buffer of 1 + 2*4000 int64 -- [0] = event counter (zero it), then (event<<32 | work,
-// clock64) pairs recorded by CTA 0 of every conv_tc2 launch while installed.  NULL uninstalls.  Not part of the product API.
+// Developer hook (tools/trace_tc2.py): zeroed device buffer of 1 + 64*64 int64 -- while installed, CTA 0 of every conv_tc2 launch
+// writes clock64() of event e of its tile iteration `it` to [1 + it*64 + e].  NULL uninstalls.  Not part of the product API.
 extern "C" int mn_debug_tc2_trace(long long* device_buffer) { g_tc2_trace = device_buffer; return 0; }
 
 int mn_conv_tc2_supported(const ConvGeom& g, const char** why) {
