@@ -34,7 +34,32 @@ SQRT2 = math.sqrt(2.0)
 
 class _CapturedCall:
     """One module forward for one input signature, recorded into a CUDA graph: static inputs, a device error flag, static outputs."""
-    __slots__ = ("graph", "inputs", "outputs", "flag")
+    __slots__ = ("graph", "inputs", "outputs", "flag", "pinned", "h2d_done")
+
+
+def _copy_sources(ent, sources):
+    """Caller tensors -> static inputs.  A pageable host tensor (the reference's CPU labels) would make ``copy_`` synchronise
+    the stream -- the host then waits for everything queued before it (e.g. the encoder's graph) and the GPU idles while Python
+    catches up -- so it is staged through a pinned buffer owned by the captured call; the event keeps the buffer from being
+    overwritten while a previous copy out of it is still in flight."""
+    staged = False
+    for i, (st, src) in enumerate(zip(ent.inputs, sources)):
+        if src.is_cuda or src.is_pinned():
+            st.copy_(src, non_blocking=True)
+            continue
+        if ent.pinned is None:
+            ent.pinned = {}
+        pin = ent.pinned.get(i)
+        if pin is None or pin.shape != src.shape or pin.dtype != src.dtype:
+            pin = ent.pinned[i] = torch.empty(tuple(src.shape), dtype=src.dtype, pin_memory=True)
+        if ent.h2d_done is not None:
+            ent.h2d_done.synchronize()
+        pin.copy_(src)
+        st.copy_(pin, non_blocking=True)
+        staged = True
+    if staged:
+        ent.h2d_done = torch.cuda.Event()
+        ent.h2d_done.record()
 
 
 class _PackedModule(nn.Module):
@@ -94,8 +119,7 @@ class _PackedModule(nn.Module):
         if fill is not None:
             fill(ent.inputs)
         else:
-            for st, src in zip(ent.inputs, sources):
-                st.copy_(src, non_blocking=True)
+            _copy_sources(ent, sources)
         ent.graph.replay()
         return ent
 
@@ -111,13 +135,13 @@ class _PackedModule(nn.Module):
         dev = next(self.parameters()).device
         try:
             ent = _CapturedCall()
+            ent.pinned = ent.h2d_done = None
             if fill is not None:
                 ent.inputs = [torch.empty(tuple(shape), dtype=dtype, device=dev) for shape, dtype in sources]
                 fill(ent.inputs)
             else:
                 ent.inputs = [torch.empty(tuple(s.shape), dtype=s.dtype, device=dev) for s in sources]
-                for st, src in zip(ent.inputs, sources):
-                    st.copy_(src, non_blocking=True)
+                _copy_sources(ent, sources)
             ent.flag = torch.zeros((1,), dtype=torch.int32, device=dev)
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))

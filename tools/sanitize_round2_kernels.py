@@ -29,6 +29,15 @@ for n, h, w, cin, cout in ((3, 32, 32, 64, 256), (1, 8, 16, 64, 64), (2, 16, 32,
         dst = torch.empty(n, h, w, cout, device=dev)
         ptrs = torch.tensor([dst[i].data_ptr() for i in reversed(range(n))], dtype=torch.int64, device=dev)
         ops.conv2d(x, cw, 3, 3, pad=(1, 1), bias=bias, out2_ptrs=ptrs)
+# fp32 CUDA-core implicit GEMM (epilogue staged through shared memory, one rolled loop): vector and scalar epilogues, strides,
+# split-K partials + reduce, residual / second output
+for n, h, w, cin, cout, k, st in ((1, 16, 64, 32, 32, 1, (1, 1)), (1, 16, 64, 64, 128, 1, (2, 1)), (2, 9, 13, 3, 5, 3, (1, 1)),
+                                  (1, 16, 32, 128, 128, 3, (2, 2)), (16, 4, 4, 64, 64, 3, (1, 1)), (1, 7, 11, 16, 130, 3, (1, 1))):
+    x = torch.randn(n, h, w, cin, device=dev)
+    wt = (torch.randn(k * k * cin, cout, device=dev) / (k * k * cin) ** 0.5).contiguous()
+    y = ops.conv2d(x, wt, k, k, stride=st, pad=(k // 2, k // 2), bias=torch.randn(cout, device=dev), act=ops.ACT_RELU, precision=ops.PREC_FP32_SIMT)
+    ops.conv2d(x, wt, k, k, stride=st, pad=(k // 2, k // 2), residual=torch.randn_like(y), out2=True, act=ops.ACT_TANH,
+               precision=ops.PREC_FP32_SIMT, split_k=3 if k == 3 else 0)
 # calibration / range guard path
 with ops.calibration(dev) as cal:
     x = torch.randn(2, 16, 16, 64, device=dev) * 1e5
