@@ -214,15 +214,28 @@ __global__ void __launch_bounds__(128) linear_small_m_kernel(const LinArgs a) {
                     wv[kk][0] = Ws[buf][k4 * 4 + kk][cg];
                 }
             }
+            // k-outer, accumulator-inner: the RPT x CPT FMAs of one k are independent, so they issue back to back; the round-1 order
+            // (four dependent FMAs per accumulator in a row) left a single warp per scheduler waiting on its own FMA latency --
+            // ~1.7k cycles per 32-deep chunk for 256 FMAs per thread.  Same summation order per accumulator: bit-identical results.
+            float4 xv[RPT];
 #pragma unroll
-            for (int i = 0; i < RPT; ++i) {
-                const float4 xv = *reinterpret_cast<const float4*>(&Xs[buf][rg * RPT + i][k4 * 4]);
+            for (int i = 0; i < RPT; ++i) xv[i] = *reinterpret_cast<const float4*>(&Xs[buf][rg * RPT + i][k4 * 4]);
 #pragma unroll
-                for (int c = 0; c < CPT; ++c) {
-                    acc[i][c] = fmaf(xv.x, wv[0][c], acc[i][c]); acc[i][c] = fmaf(xv.y, wv[1][c], acc[i][c]);
-                    acc[i][c] = fmaf(xv.z, wv[2][c], acc[i][c]); acc[i][c] = fmaf(xv.w, wv[3][c], acc[i][c]);
-                }
-            }
+            for (int i = 0; i < RPT; ++i)
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) acc[i][c] = fmaf(xv[i].x, wv[0][c], acc[i][c]);
+#pragma unroll
+            for (int i = 0; i < RPT; ++i)
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) acc[i][c] = fmaf(xv[i].y, wv[1][c], acc[i][c]);
+#pragma unroll
+            for (int i = 0; i < RPT; ++i)
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) acc[i][c] = fmaf(xv[i].z, wv[2][c], acc[i][c]);
+#pragma unroll
+            for (int i = 0; i < RPT; ++i)
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) acc[i][c] = fmaf(xv[i].w, wv[3][c], acc[i][c]);
         }
         __syncthreads();
     }
@@ -378,7 +391,9 @@ static int linear_small_m_impl(const float* x, long long x_row_stride, long long
     const int tiles = mn_cdiv(N, wide ? 64 : 16) * batches;
     // K slices (one cluster, <= 8 CTAs): spread a small layer over ~one CTA per SM, a long K over ~two
     const int sms = mn_num_sms(), chunks = K / 32;
-    const int budget = K >= 4096 ? 2 * sms : sms;
+    // (in-graph sweep, tools/bench_linear.py, profiles/r2_linear_ks_sweep.txt: these kernels are latency bound, up to 12 CTAs fit
+    // on an SM, and a 16-column tile prefers 4-chunk K slices: 64x512x1536 16.8 -> 13.1 us, 64x512x1024 11.0 -> 9.1, 64x1024x512 12.4 -> 10.8)
+    const int budget = (K >= 4096 || !wide) ? 2 * sms : sms;
     int ks = 1;
     while (ks < 8 && tiles * ks * 2 <= budget && chunks / (ks * 2) >= 2) ks *= 2;
     static int force_ks = -1;                            // developer override: MN_LIN_KS=1|2|4|8
