@@ -79,7 +79,7 @@ __global__ void gn_finalize_kernel(const double* __restrict__ stats, float2* __r
 }
 
 // One thread normalises 4 channels of GN_PPT pixels (pixel stride = a quarter of the tensor, so every warp access stays a
-// contiguous run of channels); all loads are issued before the first use.  Measured 3.4-3.9 TB/s; a capped grid-stride
+// contiguous run of channels); all loads are issued before the first use.  Measured 3.4-3.9 TB/s in round 1 (issue-bound, see below); a capped grid-stride
 // variant (8 CTAs/SM) was slower (2.7-3.0 TB/s: 56 registers leave only 4 resident CTAs), one item per thread 3.1-3.4.
 constexpr int GN_PPT = 4;
 __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x, int x_cs, float* __restrict__ y, int y_cs,
@@ -126,7 +126,9 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 float u = (t[j] - mean) * rstd * gam[j] + bet[j];
-                if (swish) u = u * (1.f / (1.f + expf(-u)));
+                // ex2.approx + IEEE-rounded reciprocal: ~2e-7 relative on the sigmoid.  expf + a full-range division cost ~25 of this
+                // kernel's ~40 instructions per element and made it ISSUE-bound at 3.9 TB/s (round 2; same transform as conv_tc2's fused path)
+                if (swish) u = u * __frcp_rn(1.f + __expf(-u));
                 t[j] = u;
             }
             o = make_float4(t[0], t[1], t[2], t[3]);
@@ -163,15 +165,29 @@ __global__ void __launch_bounds__(256) adain_stats_kernel(const float* __restric
         cnt = 0;
     };
     if (my_p < ppi && wv > 0) {
-        for (int p = p_begin + my_p; p < p_end; p += ppi) {
-            const int yy = p / wv, xx = p - yy * wv;
-            const float4 a = *reinterpret_cast<const float4*>(pr + ((size_t)yy * Wp + wn.y1 + xx) * prior_cs);
-            const float4 b = *reinterpret_cast<const float4*>(ft + ((size_t)yy * W + wn.x1 + xx) * feat_cs);
-            sp.x += a.x; sp.y += a.y; sp.z += a.z; sp.w += a.w;
-            qp.x = fmaf(a.x, a.x, qp.x); qp.y = fmaf(a.y, a.y, qp.y); qp.z = fmaf(a.z, a.z, qp.z); qp.w = fmaf(a.w, a.w, qp.w);
-            sl.x += b.x; sl.y += b.y; sl.z += b.z; sl.w += b.w;
-            ql.x = fmaf(b.x, b.x, ql.x); ql.y = fmaf(b.y, b.y, ql.y); ql.z = fmaf(b.z, b.z, ql.z); ql.w = fmaf(b.w, b.w, ql.w);
-            if (++cnt == 16) flush();
+        // four pixels per trip, all eight loads issued before the first add (two loads in flight per thread left the kernel at
+        // ~2.7 TB/s); same pixel order and flush cadence per thread, the zero-filled tail adds nothing: bit-identical sums
+        for (int p = p_begin + my_p; p < p_end; p += 4 * ppi) {
+            float4 a[4], b[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int pu = p + u * ppi;
+                a[u] = b[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (pu < p_end) {
+                    const int yy = pu / wv, xx = pu - yy * wv;
+                    a[u] = *reinterpret_cast<const float4*>(pr + ((size_t)yy * Wp + wn.y1 + xx) * prior_cs);
+                    b[u] = *reinterpret_cast<const float4*>(ft + ((size_t)yy * W + wn.x1 + xx) * feat_cs);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                sp.x += a[u].x; sp.y += a[u].y; sp.z += a[u].z; sp.w += a[u].w;
+                qp.x = fmaf(a[u].x, a[u].x, qp.x); qp.y = fmaf(a[u].y, a[u].y, qp.y); qp.z = fmaf(a[u].z, a[u].z, qp.z); qp.w = fmaf(a[u].w, a[u].w, qp.w);
+                sl.x += b[u].x; sl.y += b[u].y; sl.z += b[u].z; sl.w += b[u].w;
+                ql.x = fmaf(b[u].x, b[u].x, ql.x); ql.y = fmaf(b[u].y, b[u].y, ql.y); ql.z = fmaf(b[u].z, b[u].z, ql.z); ql.w = fmaf(b[u].w, b[u].w, ql.w);
+            }
+            cnt += 4;
+            if (cnt >= 16) flush();
         }
     }
     flush();
