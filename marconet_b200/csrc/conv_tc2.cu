@@ -89,11 +89,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t off_b = HS * t.halo_stage_bytes;
     const uint32_t off_stg = off_b + t.bstages * B_STAGE;
     const uint32_t off_rowm = off_stg + STG_BYTES;
-    const uint32_t off_gnp = off_rowm + 1024;
-    const uint32_t off_bars = off_gnp + 512;
+    const uint32_t off_bars = off_rowm + 1024;
     float* stg = reinterpret_cast<float*>(smem + off_stg);
     int* rowm = reinterpret_cast<int*>(smem + off_rowm);
-    float* gnp = reinterpret_cast<float*>(smem + off_gnp);       // gamma[64] | beta[64] of the current channel block (fused GroupNorm)
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + off_bars);
     // barrier indices
     constexpr int MAX_HS = 3;
@@ -404,79 +402,106 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         uint32_t hs = 0, hph = 0;
         constexpr bool gn = GN;       // fused GroupNorm(+swish) input transform: separate instantiation, zero cost when off
         const int G = g.Cin >> 5;
+        const int qs = sidx & 3, rs0 = sidx >> 2;            // 16-channel slice of the block, first halo row of this lane
+        const int rows_up = (t.halo_rows + 31) & ~31;        // whole warps run every trip (__syncwarp inside)
         for (int work = cluster_id; work < total_work; work += num_clusters) {
-            int hn0 = 0, hoy0 = 0, hox0 = 0;
-            if (gn) tile_origin(work, hn0, hoy0, hox0);
+            int hn0 = 0, hoy0 = 0, hox0 = 0, gvw = 0x7fffffff;
+            if (gn) {
+                tile_origin(work, hn0, hoy0, hox0);
+                if (g.valid_w && hn0 < g.N) gvw = g.valid_w[hn0];
+            }
             const int cb0 = work_ks(work) * t.cbps;
             for (int cbi = 0; cbi < t.cbps; ++cbi) {
                 const int cb = cb0 + cbi;
-                if (gn) {   // per-channel affine of this 64-channel block -> smem (the previous block's readers are past their rows)
-                    named_bar_sync(2, 128);
-                    if (sidx < 64) gnp[sidx] = g.gn_gamma[cb * KB + sidx];
-                    else gnp[sidx] = g.gn_beta[cb * KB + sidx - 64];
-                    named_bar_sync(2, 128);
+                // Four lanes per halo row: lane slice qs owns fp32 chunks 2qs, 2qs+1 of both 128-byte boxes = channels [8qs, 8qs+8) and
+                // [32+8qs, 32+8qs+8) of the block, i.e. exactly the 16-byte fp16 chunks qs and 4+qs of the hi and of the lo plane.
+                // (Round 2, first version: one lane per row -- 180 rows on 128 lanes = two passes, the second 40 % full -- and, for the
+                // fused GroupNorm, per-row global loads of mean / rstd and 48 table reads per row from shared memory, on the port that
+                // bounds the kernel.)  The GroupNorm constants of the lane's 16 channels live in registers, loaded before the wait on
+                // the halo so that their latency overlaps the TMA.
+                float gm0 = 0.f, gm1 = 0.f, ga[16], gb[16];
+                if (gn) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) { ga[e] = 0.f; gb[e] = 0.f; }
+                    if (hn0 < g.N) {
+                        const float2 mr0 = g.gn_mr[(size_t)hn0 * G + cb * 2], mr1 = g.gn_mr[(size_t)hn0 * G + cb * 2 + 1];
+                        gm0 = mr0.x; gm1 = mr1.x;
+#pragma unroll
+                        for (int hlf = 0; hlf < 2; ++hlf)
+#pragma unroll
+                            for (int f = 0; f < 2; ++f) {
+                                const int c0 = cb * KB + hlf * 32 + qs * 8 + f * 4;
+                                const float4 gg = ldg4(g.gn_gamma + c0), be = ldg4(g.gn_beta + c0);
+                                const float rs = hlf ? mr1.y : mr0.y;
+                                ga[hlf * 8 + f * 4 + 0] = rs * gg.x; ga[hlf * 8 + f * 4 + 1] = rs * gg.y;
+                                ga[hlf * 8 + f * 4 + 2] = rs * gg.z; ga[hlf * 8 + f * 4 + 3] = rs * gg.w;
+                                gb[hlf * 8 + f * 4 + 0] = be.x; gb[hlf * 8 + f * 4 + 1] = be.y; gb[hlf * 8 + f * 4 + 2] = be.z; gb[hlf * 8 + f * 4 + 3] = be.w;
+                            }
+                    }
                 }
                 mbar_wait(bar(I_HF + hs), hph);
                 if (sidx == 0) mark(2, work);            // halo landed -> split starts
                 uint8_t* halo = smem + hs * t.halo_stage_bytes;
-                for (int rho = sidx; rho < t.halo_rows; rho += 128) {
+                for (int rho = rs0; rho < rows_up; rho += 32) {
+                    const bool live = rho < t.halo_rows;
                     uint8_t* row0 = halo + rho * 128;
                     uint8_t* row1 = row0 + t.box_bytes;
                     const int sw = rho & 7;
-                    uint32_t hi[32], lo[32];
+                    const uint32_t o0 = (uint32_t)((2 * qs) ^ sw) << 4, o1 = (uint32_t)((2 * qs + 1) ^ sw) << 4;
+                    float4 v[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (live) {
+                        v[0] = *reinterpret_cast<const float4*>(row0 + o0); v[1] = *reinterpret_cast<const float4*>(row0 + o1);
+                        v[2] = *reinterpret_cast<const float4*>(row1 + o0); v[3] = *reinterpret_cast<const float4*>(row1 + o1);
+                    }
                     // fused GroupNorm(+swish): which pixel is this halo row, is it inside the image / the valid window?
                     bool inside = true;
-                    float m0 = 0.f, r0 = 1.f, m1 = 0.f, r1 = 1.f;
                     if (gn) {
-                        const int htn = rho / (t.HHt * t.HWd);
-                        const int hrem = rho - htn * (t.HHt * t.HWd);
-                        const int hy = hrem / t.HWd, hx = hrem - hy * t.HWd;
-                        const int n = hn0 + htn, y = hoy0 - t.ph + hy, x = hox0 - t.pw + hx;
-                        inside = n < g.N && (unsigned)y < (unsigned)g.H && (unsigned)x < (unsigned)g.W && (!g.valid_w || x < g.valid_w[n]);
-                        if (inside) {
-                            const float2 a = g.gn_mr[(size_t)n * G + cb * 2], b2 = g.gn_mr[(size_t)n * G + cb * 2 + 1];
-                            m0 = a.x; r0 = a.y; m1 = b2.x; r1 = b2.y;
-                        }
+                        const int hy = rho / t.HWd, hx = rho - hy * t.HWd;          // one sample per tile (plan: TN == 1)
+                        const int y = hoy0 - t.ph + hy, x = hox0 - t.pw + hx;
+                        inside = hn0 < g.N && (unsigned)y < (unsigned)g.H && (unsigned)x < (unsigned)g.W && x < gvw;
                     }
+                    uint32_t hw[8], lw[8];          // hi / lo words: [0..3] = chunk qs, [4..7] = chunk 4+qs
 #pragma unroll
-                    for (int box = 0; box < 2; ++box) {
-                        const uint8_t* bsrc = box ? row1 : row0;
+                    for (int k = 0; k < 4; ++k) {
+                        float tt[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+                        if (gn) {
+                            const float mean = (k >> 1) ? gm1 : gm0;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            float4 v = *reinterpret_cast<const float4*>(bsrc + ((j ^ sw) << 4));
-                            if (gn) {
-                                const float mean = box ? m1 : m0, rstd = box ? r1 : r0;
-                                const float4 ga = *reinterpret_cast<const float4*>(&gnp[box * 32 + j * 4]);
-                                const float4 be = *reinterpret_cast<const float4*>(&gnp[64 + box * 32 + j * 4]);
-                                float tt[4] = {v.x, v.y, v.z, v.w};
-                                const float gg[4] = {ga.x, ga.y, ga.z, ga.w}, bb[4] = {be.x, be.y, be.z, be.w};
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    float u = (tt[e] - mean) * rstd * gg[e] + bb[e];
-                                    if (g.gn_swish) u = u * __frcp_rn(1.f + __expf(-u));     // ex2.approx + rcp: ~1e-7 relative on the sigmoid
-                                    tt[e] = inside ? u : 0.f;
-                                }
-                                v = make_float4(tt[0], tt[1], tt[2], tt[3]);
-                            }
-                            v.x *= xs; v.y *= xs; v.z *= xs; v.w *= xs;
-                            amax = fmaxf(fmaxf(amax, fabsf(v.x)), fmaxf(fabsf(v.y), fmaxf(fabsf(v.z), fabsf(v.w))));   // 4 FMNMX (|.| is a free modifier)
-                            const float h0 = __uint_as_float(__float_as_uint(v.x) & mask), h1 = __uint_as_float(__float_as_uint(v.y) & mask);
-                            const float h2 = __uint_as_float(__float_as_uint(v.z) & mask), h3 = __uint_as_float(__float_as_uint(v.w) & mask);
-                            const int c = box * 16 + j * 2;
-                            if (bf) {
-                                hi[c] = pack_bf16(h0, h1); hi[c + 1] = pack_bf16(h2, h3);
-                                lo[c] = pack_bf16(v.x - h0, v.y - h1); lo[c + 1] = pack_bf16(v.z - h2, v.w - h3);
-                            } else {
-                                hi[c] = pack_f16(h0, h1); hi[c + 1] = pack_f16(h2, h3);
-                                lo[c] = pack_f16(v.x - h0, v.y - h1); lo[c + 1] = pack_f16(v.z - h2, v.w - h3);
+                            for (int e = 0; e < 4; ++e) {
+                                float u = fmaf(tt[e] - mean, ga[k * 4 + e], gb[k * 4 + e]);
+                                if (g.gn_swish) u = __fdividef(u, 1.f + __expf(-u));     // ex2.approx + rcp.approx: ~2e-7 relative on the sigmoid
+                                tt[e] = inside ? u : 0.f;
                             }
                         }
-                    }
-                    // all 256 B of this row are in registers now: overwrite it (row0 <- hi plane, row1 <- lo plane)
 #pragma unroll
-                    for (int jj = 0; jj < 8; ++jj) {
-                        *reinterpret_cast<uint4*>(row0 + ((jj ^ sw) << 4)) = make_uint4(hi[4 * jj], hi[4 * jj + 1], hi[4 * jj + 2], hi[4 * jj + 3]);
-                        *reinterpret_cast<uint4*>(row1 + ((jj ^ sw) << 4)) = make_uint4(lo[4 * jj], lo[4 * jj + 1], lo[4 * jj + 2], lo[4 * jj + 3]);
+                        for (int e = 0; e < 4; ++e) tt[e] *= xs;
+                        amax = fmaxf(fmaxf(amax, fabsf(tt[0])), fmaxf(fabsf(tt[1]), fmaxf(fabsf(tt[2]), fabsf(tt[3]))));   // 4 FMNMX (|.| is a free modifier)
+                        const float h0 = __uint_as_float(__float_as_uint(tt[0]) & mask), h1 = __uint_as_float(__float_as_uint(tt[1]) & mask);
+                        const float h2 = __uint_as_float(__float_as_uint(tt[2]) & mask), h3 = __uint_as_float(__float_as_uint(tt[3]) & mask);
+                        if (bf) {
+                            hw[2 * k] = pack_bf16(h0, h1); hw[2 * k + 1] = pack_bf16(h2, h3);
+                            lw[2 * k] = pack_bf16(tt[0] - h0, tt[1] - h1); lw[2 * k + 1] = pack_bf16(tt[2] - h2, tt[3] - h3);
+                        } else {
+                            hw[2 * k] = pack_f16(h0, h1); hw[2 * k + 1] = pack_f16(h2, h3);
+                            lw[2 * k] = pack_f16(tt[0] - h0, tt[1] - h1); lw[2 * k + 1] = pack_f16(tt[2] - h2, tt[3] - h3);
+                        }
+                    }
+                    // the four lanes of a row (same warp) have read all 256 bytes of it: overwrite in place (row0 <- hi plane, row1 <- lo plane).
+                    // Odd rows store their upper chunk first: the two rows of a quarter-warp then hit disjoint banks.
+                    __syncwarp();
+                    if (live) {
+                        const uint32_t ca = (uint32_t)(qs ^ sw) << 4, cb2 = (uint32_t)((4 + qs) ^ sw) << 4;
+                        const uint4 ha = make_uint4(hw[0], hw[1], hw[2], hw[3]), hb = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+                        const uint4 la = make_uint4(lw[0], lw[1], lw[2], lw[3]), lb = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+                        if (rho & 1) {
+                            *reinterpret_cast<uint4*>(row0 + cb2) = hb; *reinterpret_cast<uint4*>(row0 + ca) = ha;
+                            *reinterpret_cast<uint4*>(row1 + cb2) = lb; *reinterpret_cast<uint4*>(row1 + ca) = la;
+                        } else {
+                            *reinterpret_cast<uint4*>(row0 + ca) = ha; *reinterpret_cast<uint4*>(row0 + cb2) = hb;
+                            *reinterpret_cast<uint4*>(row1 + ca) = la; *reinterpret_cast<uint4*>(row1 + cb2) = lb;
+                        }
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // these generic writes precede the next TMA refill
@@ -668,6 +693,7 @@ Tc2Plan plan_tc2(const ConvGeom& g) {
     if (t.halo_rows > 208) return fail("halo tile too large for shared memory");
     if ((g.y2_ptrs || g.gn_stats_out) && t.TN != 1)
         return fail("per-sample output pointers / epilogue GroupNorm statistics need samples of at least one whole pixel tile (OH*OW >= 128)");
+    if (g.gn_mr && t.TN != 1) return fail("fused GroupNorm input transform needs samples of at least one whole pixel tile (H*W >= 128)");
     if (t.HWd > 256 || t.HHt > 256 || t.TN > 256) return fail("TMA box dim");
     t.box_bytes = (t.halo_rows * 128 + 1023) & ~1023;
     t.halo_stage_bytes = 2 * t.box_bytes;
@@ -706,7 +732,7 @@ Tc2Plan plan_tc2(const ConvGeom& g) {
     if (force_hs < 0) { const char* e = getenv("MN_TC_HALO_STAGES"); force_hs = e ? atoi(e) : 0; }
     if (force_epi < -1) { const char* e = getenv("MN_TC_EPI_CB"); force_epi = e ? atoi(e) : -1; }
     const int b_stage_bytes = 2 * (p.NT / t.cg) * 128;
-    const int other = STG_BYTES + 1024 + 512 + 256 + 1024;
+    const int other = STG_BYTES + 1024 + 256 + 1024;
     t.hstages = 2;
     {
         const bool fits3 = 3 * t.halo_stage_bytes + other + 3 * b_stage_bytes <= SMEM_LIMIT;

@@ -328,7 +328,13 @@ def _note_fallback(cw, key, flop, p):
     logging.getLogger("marconet_b200").info("conv %s %s runs on the fp32 CUDA-core kernel: %s", name, key, reason)
 
 
-FUSE_GN = _os.environ.get("MN_FUSE_GN", "0") == "1"
+# fused GroupNorm(+swish) input transform of the tcgen05 conv (MN_FUSE_GN): "1" (default) every layer that kernel runs, "0" never
+# (mn_groupnorm_apply writes a normalised copy first), "auto" only the layers with 128-wide tiles (Cout % 128 == 0)
+FUSE_GN = {"0": 0, "1": 1, "auto": 2, "2": 2}.get(_os.environ.get("MN_FUSE_GN", "1"), 1)
+
+
+def _fuse_gn(cout):
+    return FUSE_GN == 1 or (FUSE_GN == 2 and cout % 128 == 0)
 TC_MIN_FLOP = 3.0e7    # tiny launches are latency-bound either way and stay on the exact fp32 path
 
 
@@ -338,8 +344,9 @@ def conv2d(x, w, kh, kw, stride=(1, 1), pad=(0, 0), bias=None, out_scale=None, r
     """mn_conv2d_nhwc.  ``w`` is the packed [KH*KW*Cin, Cout] matrix.  Returns y (or (y, y2)).
     ``gn=(mean_rstd, gamma, beta)``: the conv input is swish(GroupNorm(x)); fused into the tcgen05 v2 kernel's operand-split
     stage when ``gn_fuse`` is true and that kernel runs the layer, otherwise applied by mn_groupnorm_apply first.
-    (Measured on B200: with 4 split warps per CTA the fused transform makes the split stage the bottleneck -- 8.7 vs 7.1 ms per
-    line in round 2 -- so the default policy FUSE_GN is off; the kernel path stays tested for a wider split stage.)
+    (Default on since the split stage runs four lanes per halo row with the GroupNorm constants in registers: 6.30 vs 6.32 ms per
+    line, TSPSRNet graph 3.73 vs 3.86 ms, all eight normalise passes gone; its first form -- one lane per row, per-row global loads of
+    mean / rstd -- measured 8.7 vs 7.1 ms.)
     ``gn_stats=True``: also return the GroupNorm statistics (mean / rstd [N, Cout/32, 2]) of the OUTPUT, for the GroupNorm that
     follows this conv (networks.py:508-512): accumulated by the tcgen05 kernel's epilogue (mn_conv_params.gn_stats_out, no read
     pass over y) when that kernel runs the layer, by mn_groupnorm_stats otherwise.  Returns (y, mean_rstd)."""
@@ -408,7 +415,7 @@ def conv2d(x, w, kh, kw, stride=(1, 1), pad=(0, 0), bias=None, out_scale=None, r
             calib = getattr(_TLS, "calib", None)
             if calib is not None:
                 p.x_absmax = calib.slot(cw).data_ptr()
-            if gn is not None and ver == 2 and (FUSE_GN if gn_fuse is None else gn_fuse):
+            if gn is not None and ver == 2 and (_fuse_gn(cout) if gn_fuse is None else gn_fuse):
                 p.gn_mean_rstd = gn[0].data_ptr(); p.gn_gamma = gn[1].data_ptr(); p.gn_beta = gn[2].data_ptr(); p.gn_swish = 1
                 gn_fused = True
         elif precision is not None:
