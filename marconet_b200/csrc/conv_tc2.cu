@@ -413,7 +413,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const int cb0 = work_ks(work) * t.cbps;
             for (int cbi = 0; cbi < t.cbps; ++cbi) {
                 const int cb = cb0 + cbi;
-                // Four lanes per halo row: lane slice qs owns fp32 chunks 2qs, 2qs+1 of both 128-byte boxes = channels [8qs, 8qs+8) and
+                // Fused GroupNorm instantiation -- four lanes per halo row: lane slice qs owns fp32 chunks 2qs, 2qs+1 of both 128-byte boxes = channels [8qs, 8qs+8) and
                 // [32+8qs, 32+8qs+8) of the block, i.e. exactly the 16-byte fp16 chunks qs and 4+qs of the hi and of the lo plane.
                 // (Round 2, first version: one lane per row -- 180 rows on 128 lanes = two passes, the second 40 % full -- and, for the
                 // fused GroupNorm, per-row global loads of mean / rstd and 48 table reads per row from shared memory, on the port that
@@ -442,6 +442,44 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 mbar_wait(bar(I_HF + hs), hph);
                 if (sidx == 0) mark(2, work);            // halo landed -> split starts
                 uint8_t* halo = smem + hs * t.halo_stage_bytes;
+                if constexpr (!GN) {
+                    // Plain split: ONE lane per halo row (two passes over <= 208 rows, the second partly idle).  Same-box A/B (driver
+                    // arguments, tools/gpu_run32.sh): the four-lanes-per-row form below spends ~35 % more issue slots on the same work (per-trip
+                    // overhead on 16 instead of 64 channels; no idle warps) and costs the feed warps 0.11 ms per line; without a transform to
+                    // hide there is nothing to gain from it.
+                    for (int rho = sidx; rho < t.halo_rows; rho += 128) {
+                        uint8_t* row0 = halo + rho * 128;
+                        uint8_t* row1 = row0 + t.box_bytes;
+                        const int sw = rho & 7;
+                        uint32_t hi[32], lo[32];
+#pragma unroll
+                        for (int box = 0; box < 2; ++box) {
+                            const uint8_t* bsrc = box ? row1 : row0;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                float4 v = *reinterpret_cast<const float4*>(bsrc + ((j ^ sw) << 4));
+                                v.x *= xs; v.y *= xs; v.z *= xs; v.w *= xs;
+                                amax = fmaxf(fmaxf(amax, fabsf(v.x)), fmaxf(fabsf(v.y), fmaxf(fabsf(v.z), fabsf(v.w))));   // 4 FMNMX (|.| is a free modifier)
+                                const float h0 = __uint_as_float(__float_as_uint(v.x) & mask), h1 = __uint_as_float(__float_as_uint(v.y) & mask);
+                                const float h2 = __uint_as_float(__float_as_uint(v.z) & mask), h3 = __uint_as_float(__float_as_uint(v.w) & mask);
+                                const int c = box * 16 + j * 2;
+                                if (bf) {
+                                    hi[c] = pack_bf16(h0, h1); hi[c + 1] = pack_bf16(h2, h3);
+                                    lo[c] = pack_bf16(v.x - h0, v.y - h1); lo[c + 1] = pack_bf16(v.z - h2, v.w - h3);
+                                } else {
+                                    hi[c] = pack_f16(h0, h1); hi[c + 1] = pack_f16(h2, h3);
+                                    lo[c] = pack_f16(v.x - h0, v.y - h1); lo[c + 1] = pack_f16(v.z - h2, v.w - h3);
+                                }
+                            }
+                        }
+                        // all 256 B of this row are in registers now: overwrite it (row0 <- hi plane, row1 <- lo plane)
+#pragma unroll
+                        for (int jj = 0; jj < 8; ++jj) {
+                            *reinterpret_cast<uint4*>(row0 + ((jj ^ sw) << 4)) = make_uint4(hi[4 * jj], hi[4 * jj + 1], hi[4 * jj + 2], hi[4 * jj + 3]);
+                            *reinterpret_cast<uint4*>(row1 + ((jj ^ sw) << 4)) = make_uint4(lo[4 * jj], lo[4 * jj + 1], lo[4 * jj + 2], lo[4 * jj + 3]);
+                        }
+                    }
+                } else
                 for (int rho = rs0; rho < rows_up; rho += 32) {
                     const bool live = rho < t.halo_rows;
                     uint8_t* row0 = halo + rho * 128;
@@ -495,13 +533,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         const uint32_t ca = (uint32_t)(qs ^ sw) << 4, cb2 = (uint32_t)((4 + qs) ^ sw) << 4;
                         const uint4 ha = make_uint4(hw[0], hw[1], hw[2], hw[3]), hb = make_uint4(hw[4], hw[5], hw[6], hw[7]);
                         const uint4 la = make_uint4(lw[0], lw[1], lw[2], lw[3]), lb = make_uint4(lw[4], lw[5], lw[6], lw[7]);
-                        if (rho & 1) {
-                            *reinterpret_cast<uint4*>(row0 + cb2) = hb; *reinterpret_cast<uint4*>(row0 + ca) = ha;
-                            *reinterpret_cast<uint4*>(row1 + cb2) = lb; *reinterpret_cast<uint4*>(row1 + ca) = la;
-                        } else {
-                            *reinterpret_cast<uint4*>(row0 + ca) = ha; *reinterpret_cast<uint4*>(row0 + cb2) = hb;
-                            *reinterpret_cast<uint4*>(row1 + ca) = la; *reinterpret_cast<uint4*>(row1 + cb2) = lb;
-                        }
+                        // selects, not a branch: a divergent warp would issue every store twice with half the lanes (2x the wavefronts
+                        // -- measured: +10 % LSU shared wavefronts on the roofline layer)
+                        const bool odd = (rho & 1) != 0;
+                        const uint32_t c1 = odd ? cb2 : ca, c2 = odd ? ca : cb2;
+                        const uint4 h1 = odd ? hb : ha, h2 = odd ? ha : hb, l1 = odd ? lb : la, l2 = odd ? la : lb;
+                        *reinterpret_cast<uint4*>(row0 + c1) = h1; *reinterpret_cast<uint4*>(row1 + c1) = l1;
+                        *reinterpret_cast<uint4*>(row0 + c2) = h2; *reinterpret_cast<uint4*>(row1 + c2) = l2;
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // these generic writes precede the next TMA refill
