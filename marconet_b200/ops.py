@@ -344,9 +344,9 @@ def conv2d(x, w, kh, kw, stride=(1, 1), pad=(0, 0), bias=None, out_scale=None, r
     """mn_conv2d_nhwc.  ``w`` is the packed [KH*KW*Cin, Cout] matrix.  Returns y (or (y, y2)).
     ``gn=(mean_rstd, gamma, beta)``: the conv input is swish(GroupNorm(x)); fused into the tcgen05 v2 kernel's operand-split
     stage when ``gn_fuse`` is true and that kernel runs the layer, otherwise applied by mn_groupnorm_apply first.
-    (Default on since the split stage runs four lanes per halo row with the GroupNorm constants in registers: 6.30 vs 6.32 ms per
-    line, TSPSRNet graph 3.73 vs 3.86 ms, all eight normalise passes gone; its first form -- one lane per row, per-row global loads of
-    mean / rstd -- measured 8.7 vs 7.1 ms.)
+    (Default on since the fused instantiation runs four lanes per halo row with the GroupNorm constants in registers: all eight
+    normalise passes gone, 1.3 % per line on the same box, profiles/r2_split_gn_ab.txt; its first form -- one lane per row, per-row
+    global loads of mean / rstd -- measured 8.7 vs 7.1 ms.)
     ``gn_stats=True``: also return the GroupNorm statistics (mean / rstd [N, Cout/32, 2]) of the OUTPUT, for the GroupNorm that
     follows this conv (networks.py:508-512): accumulated by the tcgen05 kernel's epilogue (mn_conv_params.gn_stats_out, no read
     pass over y) when that kernel runs the layer, by mn_groupnorm_stats otherwise.  Returns (y, mean_rstd)."""
