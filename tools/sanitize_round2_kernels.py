@@ -24,7 +24,10 @@ for n, h, w, cin, cout in ((3, 32, 32, 64, 256), (1, 8, 16, 64, 64), (2, 16, 32,
         ops.conv2d(x, cw, 3, 3, pad=(1, 1), bias=bias, out_scale=torch.rand(n, cout, device=dev), out2=True, y2_scale=torch.rand(n, cout, device=dev),
                    residual=torch.randn(n, h, w, cout, device=dev), act=ops.ACT_TANH, precision=prec)
     if h * w >= 128 and 2.0 * n * h * w * cout * 9 * cin >= ops.TC_MIN_FLOP:     # layers the tensor-core kernel runs (peer pointers need it)
-        ops.conv2d(x, cw, 3, 3, pad=(1, 1), bias=bias, valid_w=vw, gn_stats=True)
+        y1, mr = ops.conv2d(x, cw, 3, 3, pad=(1, 1), bias=bias, valid_w=vw, gn_stats=True)
+        # fused GroupNorm+swish operand transform (four lanes per halo row, in-place overwrite ordered by __syncwarp) on that output
+        cw2 = ops.ConvWeight((torch.randn(9 * cout, cout, device=dev) / (9 * cout) ** 0.5).contiguous(), 9, name=f"san.gn.{n}.{h}.{cout}")
+        ops.conv2d(y1, cw2, 3, 3, pad=(1, 1), bias=bias, valid_w=vw, gn=(mr, torch.rand(cout, device=dev) + 0.5, torch.randn(cout, device=dev)), gn_fuse=True)
         # per-sample destination pointers of the second output (local memory standing in for a peer's)
         dst = torch.empty(n, h, w, cout, device=dev)
         ptrs = torch.tensor([dst[i].data_ptr() for i in reversed(range(n))], dtype=torch.int64, device=dev)
