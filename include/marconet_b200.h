@@ -101,7 +101,9 @@ typedef struct {
     const float* w_tc_scale;                   /* the 2-float scale record written by the packer */
     /* optional input transform fused into the tcgen05 v2 kernel's operand-split stage (mn_conv2d_tc_version() == 2 only):
      *   x' = swish( (x - mean[n,g]) * rstd[n,g] * gamma[c] + beta[c] ),  zero outside the image / beyond valid_w[n]
-     * i.e. GroupNorm(32 channels per group) + swish of models/networks.py:508-512 applied while the A operand is built.  */
+     * i.e. GroupNorm(32 channels per group) + swish of models/networks.py:508-512 applied while the A operand is built (its own
+     * kernel instantiation: four lanes per halo row, constants in registers).  Needs OH*OW >= 128 (one sample per 128-pixel tile);
+     * the sigmoid uses ex2.approx / rcp.approx (~2e-7 relative).  */
     const float* gn_mean_rstd;                 /* [N][Cin/32][2] from mn_groupnorm_stats, or NULL                          */
     const float* gn_gamma; const float* gn_beta;   /* [Cin]                                                                */
     int gn_swish;
