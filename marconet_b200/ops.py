@@ -415,7 +415,7 @@ def conv2d(x, w, kh, kw, stride=(1, 1), pad=(0, 0), bias=None, out_scale=None, r
             calib = getattr(_TLS, "calib", None)
             if calib is not None:
                 p.x_absmax = calib.slot(cw).data_ptr()
-            if gn is not None and ver == 2 and (_fuse_gn(cout) if gn_fuse is None else gn_fuse):
+            if gn is not None and ver == 2 and h * wd >= 128 and (_fuse_gn(cout) if gn_fuse is None else gn_fuse):   # one sample per 128-pixel tile
                 p.gn_mean_rstd = gn[0].data_ptr(); p.gn_gamma = gn[1].data_ptr(); p.gn_beta = gn[2].data_ptr(); p.gn_swish = 1
                 gn_fused = True
         elif precision is not None:

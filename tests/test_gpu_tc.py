@@ -99,14 +99,18 @@ def test_conv_tc_epilogue_and_slices():
             assert y[i, :, :, v:].abs().max().item() == 0
 
 
+@pytest.mark.parametrize("shape", [(3, 32, 32, 128, 128), (1, 16, 256, 64, 64), (5, 16, 16, 256, 128), (2, 8, 8, 64, 64)],
+                         ids=["n3_32x32_128to128", "n1_16x256_64to64", "n5_16x16_256to128", "n2_8x8_two_pass_fallback"])
 @pytest.mark.parametrize("ragged", [False, True])
-def test_conv_tc_fused_groupnorm_swish(ragged):
-    """swish(GroupNorm(x)) built inside the conv's operand-split stage == the standalone GroupNorm kernel + conv."""
+def test_conv_tc_fused_groupnorm_swish(ragged, shape):
+    """swish(GroupNorm(x)) built inside the conv's operand-split stage == GroupNorm + swish + conv in fp64: 128- and 64-wide tiles,
+    several channel blocks, an odd number of samples (padding CTA of the last pair), ragged windows; maps smaller than one 128-pixel
+    tile (8x8) take the two-pass form transparently."""
     from marconet_b200 import ops
     d = _dev()
-    n, h, w, cin, cout = 3, 32, 32, 128, 128
+    n, h, w, cin, cout = shape
     x = _rand(n, cin, h, w, seed=20) * 2 + 0.3
-    valid = [32, 17, 5] if ragged else None
+    valid = [w, max(1, w // 2 + 1), 5, w - 1, 1][:n] if ragged else None
     if ragged:
         for i, v in enumerate(valid):
             x[i, :, :, v:] = 0
