@@ -398,7 +398,6 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             // 122 registers per thread at 480 threads, no spills.
             for (int work = cluster_id; work < total_work; work += num_clusters) epilogue(work);
         } else {
-        int prev_work = -1;
         uint32_t hs = 0, hph = 0;
         constexpr bool gn = GN;       // fused GroupNorm(+swish) input transform: separate instantiation, zero cost when off
         const int G = g.Cin >> 5;
@@ -546,9 +545,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (sidx == 0) mark(3, work);            // split done
                 mbar_arrive(bar(I_SD + hs));
                 if (++hs == (uint32_t)HS) { hs = 0; hph ^= 1; }
-                (void)prev_work;
             }
-            prev_work = work;
         }
         conv_range_report(g, __float_as_uint(amax), t.prec == MN_PREC_F16X3_TC || t.prec == MN_PREC_F16X1_TC);
         }

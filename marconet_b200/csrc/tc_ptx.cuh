@@ -181,21 +181,6 @@ __device__ __forceinline__ void tma_load_3d_cg2(const CUtensorMap* map, uint32_t
         ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
-// wait with cluster-scope acquire: for barriers that also receive arrivals from the peer CTA
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    const long long t_start = clock64();
-    for (uint32_t it = 0; !done; ++it) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (!done && (it & 1023u) == 1023u && clock64() - t_start > 4000000000ll) __trap();
-    }
-}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 }  // namespace tcptx
